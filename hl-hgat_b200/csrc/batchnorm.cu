@@ -1,0 +1,280 @@
+// Training-mode BatchNorm over rows fused with the activation and with the strided store into the
+// dense-connection buffer (hl_bn_act_fwd / hl_bn_act_bwd).  Deterministic two-stage column
+// reductions: per-block shifted sums (numerically the "shifted data" variance algorithm), merged
+// in fp64 in a fixed order.  No atomics.
+#include "common.cuh"
+
+namespace hl {
+
+constexpr int kBnThreads = 256;
+constexpr int kBnWarps = kBnThreads / 32;
+constexpr int kBnRowsPerBlock = 128;
+
+static inline int bn_row_blocks(int32_t nrows) { return (nrows + kBnRowsPerBlock - 1) / kBnRowsPerBlock; }
+
+// partial[(blk * 2 + {0,1}) * width + col] = {mean_b, M2_b} of the block's rows (fp64)
+template <int V>
+__global__ void __launch_bounds__(kBnThreads)
+bn_stats_partial_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows, int32_t width,
+                        double* __restrict__ partial) {
+  __shared__ float sh[2][kBnWarps][32 * V];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.y * (32 * V) + lane * V;
+  const int r0 = blockIdx.x * kBnRowsPerBlock;
+  const int r1 = min(r0 + kBnRowsPerBlock, nrows);
+  const bool act = col < width;
+  Pack<V> shift, s1, s2;
+#pragma unroll
+  for (int i = 0; i < V; ++i) shift.v[i] = s1.v[i] = s2.v[i] = 0.f;
+  if (act) {
+    shift = ld_pack<V>(x + (int64_t)r0 * ld_x + col);
+    for (int r = r0 + warp; r < r1; r += kBnWarps) {
+      Pack<V> v = ld_pack<V>(x + (int64_t)r * ld_x + col);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float d = v.v[i] - shift.v[i];
+        s1.v[i] += d;
+        s2.v[i] = fmaf(d, d, s2.v[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    sh[0][warp][lane * V + i] = s1.v[i];
+    sh[1][warp][lane * V + i] = s2.v[i];
+  }
+  __syncthreads();
+  if (warp == 0 && act) {
+    const double n = (double)(r1 - r0);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int w = 0; w < kBnWarps; ++w) {
+        a += (double)sh[0][w][lane * V + i];
+        b += (double)sh[1][w][lane * V + i];
+      }
+      partial[((int64_t)blockIdx.x * 2 + 0) * width + col + i] = (double)shift.v[i] + a / n;
+      partial[((int64_t)blockIdx.x * 2 + 1) * width + col + i] = b - a * a / n;
+    }
+  }
+}
+
+__global__ void bn_stats_final_kernel(const double* __restrict__ partial, int nblk, int32_t nrows, int32_t width,
+                                      float* __restrict__ stats) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= width) return;
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  for (int b = 0; b < nblk; ++b) {                            // Chan et al. pairwise merge, fixed order
+    const double nb = (double)(min((b + 1) * kBnRowsPerBlock, nrows) - b * kBnRowsPerBlock);
+    const double mb = partial[((int64_t)b * 2 + 0) * width + c];
+    const double qb = partial[((int64_t)b * 2 + 1) * width + c];
+    const double tot = n + nb;
+    const double delta = mb - mean;
+    mean += delta * nb / tot;
+    m2 += qb + delta * delta * n * nb / tot;
+    n = tot;
+  }
+  stats[c] = (float)mean;
+  stats[width + c] = (float)(m2 / n);
+}
+
+template <int V>
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows, int32_t width,
+                const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
+                float eps, float slope, float* __restrict__ y, int64_t ld_y) {
+  const int chunks = width / V;
+  const int64_t total = (int64_t)nrows * chunks;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / chunks);
+    const int col = (int)(idx - (int64_t)r * chunks) * V;
+    Pack<V> v = ld_pack<V>(x + (int64_t)r * ld_x + col);
+    Pack<V> o;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float mean = __ldg(stats + col + i);
+      const float rstd = rsqrtf(__ldg(stats + width + col + i) + eps);
+      const float g = gamma ? __ldg(gamma + col + i) : 1.f;
+      const float b = beta ? __ldg(beta + col + i) : 0.f;
+      float t = (v.v[i] - mean) * rstd * g + b;
+      o.v[i] = t > 0.f ? t : t * slope;
+    }
+    st_pack<V>(y + (int64_t)r * ld_y + col, o);
+  }
+}
+
+// backward stage 1: partial column sums of dz and dz * xhat (dz = dy * act'(y))
+template <int V>
+__global__ void __launch_bounds__(kBnThreads)
+bn_bwd_partial_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ y, int64_t ld_y,
+                      const float* __restrict__ dy, int64_t ld_dy, int32_t nrows, int32_t width,
+                      const float* __restrict__ stats, float eps, float slope, double* __restrict__ partial) {
+  __shared__ float sh[2][kBnWarps][32 * V];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.y * (32 * V) + lane * V;
+  const int r0 = blockIdx.x * kBnRowsPerBlock;
+  const int r1 = min(r0 + kBnRowsPerBlock, nrows);
+  const bool act = col < width;
+  Pack<V> s1, s2;
+#pragma unroll
+  for (int i = 0; i < V; ++i) s1.v[i] = s2.v[i] = 0.f;
+  if (act) {
+    float mean[V], rstd[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      mean[i] = __ldg(stats + col + i);
+      rstd[i] = rsqrtf(__ldg(stats + width + col + i) + eps);
+    }
+    for (int r = r0 + warp; r < r1; r += kBnWarps) {
+      Pack<V> xv = ld_pack<V>(x + (int64_t)r * ld_x + col);
+      Pack<V> yv = ld_pack<V>(y + (int64_t)r * ld_y + col);
+      Pack<V> gv = ld_pack<V>(dy + (int64_t)r * ld_dy + col);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float dz = yv.v[i] > 0.f ? gv.v[i] : gv.v[i] * slope;
+        s1.v[i] += dz;
+        s2.v[i] = fmaf(dz, (xv.v[i] - mean[i]) * rstd[i], s2.v[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    sh[0][warp][lane * V + i] = s1.v[i];
+    sh[1][warp][lane * V + i] = s2.v[i];
+  }
+  __syncthreads();
+  if (warp == 0 && act) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int w = 0; w < kBnWarps; ++w) {
+        a += (double)sh[0][w][lane * V + i];
+        b += (double)sh[1][w][lane * V + i];
+      }
+      partial[((int64_t)blockIdx.x * 2 + 0) * width + col + i] = a;
+      partial[((int64_t)blockIdx.x * 2 + 1) * width + col + i] = b;
+    }
+  }
+}
+
+// sums[0:F] = sum dz (= dbeta), sums[F:2F] = sum dz*xhat (= dgamma)
+__global__ void bn_bwd_final_kernel(const double* __restrict__ partial, int nblk, int32_t width,
+                                    float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= width) return;
+  double a = 0.0, b = 0.0;
+  for (int k = 0; k < nblk; ++k) {
+    a += partial[((int64_t)k * 2 + 0) * width + c];
+    b += partial[((int64_t)k * 2 + 1) * width + c];
+  }
+  sums[c] = (float)a;
+  sums[width + c] = (float)b;
+  if (dbeta) dbeta[c] = (float)a;
+  if (dgamma) dgamma[c] = (float)b;
+}
+
+template <int V>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ y, int64_t ld_y,
+                    const float* __restrict__ dy, int64_t ld_dy, int32_t nrows, int32_t width,
+                    const float* __restrict__ gamma, const float* __restrict__ stats, const float* __restrict__ sums,
+                    float eps, float slope, float* __restrict__ dx, int64_t ld_dx) {
+  const int chunks = width / V;
+  const int64_t total = (int64_t)nrows * chunks;
+  const float inv_n = 1.f / (float)nrows;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / chunks);
+    const int col = (int)(idx - (int64_t)r * chunks) * V;
+    Pack<V> xv = ld_pack<V>(x + (int64_t)r * ld_x + col);
+    Pack<V> yv = ld_pack<V>(y + (int64_t)r * ld_y + col);
+    Pack<V> gv = ld_pack<V>(dy + (int64_t)r * ld_dy + col);
+    Pack<V> o;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float mean = __ldg(stats + col + i);
+      const float rstd = rsqrtf(__ldg(stats + width + col + i) + eps);
+      const float g = gamma ? __ldg(gamma + col + i) : 1.f;
+      const float dz = yv.v[i] > 0.f ? gv.v[i] : gv.v[i] * slope;
+      const float xh = (xv.v[i] - mean) * rstd;
+      o.v[i] = g * rstd * (dz - __ldg(sums + col + i) * inv_n - xh * __ldg(sums + width + col + i) * inv_n);
+    }
+    st_pack<V>(dx + (int64_t)r * ld_dx + col, o);
+  }
+}
+
+static int ew_grid(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  const int64_t cap = 148LL * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace hl
+
+extern "C" size_t hl_bn_workspace(int32_t nrows, int32_t width) {
+  if (nrows < 0 || width < 0) return 0;
+  return hl::align_up((size_t)hl::bn_row_blocks(nrows > 0 ? nrows : 1) * 2 * (size_t)width * sizeof(double), 256) +
+         hl::align_up(2 * (size_t)width * sizeof(float), 256);
+}
+
+extern "C" int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_t width,
+                             const float* gamma, const float* beta, float eps, float slope,
+                             float* y, int64_t ld_y, float* stats, void* workspace, size_t workspace_bytes,
+                             hl_stream_t stream) {
+  using namespace hl;
+  if (nrows < 1 || width < 1 || !x || !y || !stats) return HL_ERR_INVALID;
+  if (!workspace || workspace_bytes < hl_bn_workspace(nrows, width)) return HL_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  double* partial = reinterpret_cast<double*>(workspace);
+  int V = vec_for(x, ld_x, width, 4);
+  V = min(V, vec_for(y, ld_y, width, V));
+  const int nblk = bn_row_blocks(nrows);
+  dim3 grid(nblk, (width + 32 * V - 1) / (32 * V));
+  if (V == 4) bn_stats_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, width, partial);
+  else if (V == 2) bn_stats_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, width, partial);
+  else bn_stats_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, width, partial);
+  HL_LAUNCH_CHECK("bn_stats_partial_kernel");
+  bn_stats_final_kernel<<<(width + 127) / 128, 128, 0, st>>>(partial, nblk, nrows, width, stats);
+  HL_LAUNCH_CHECK("bn_stats_final_kernel");
+  const int g = ew_grid((int64_t)nrows * (width / V));
+  if (V == 4) bn_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, nrows, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else if (V == 2) bn_apply_kernel<2><<<g, 256, 0, st>>>(x, ld_x, nrows, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else bn_apply_kernel<1><<<g, 256, 0, st>>>(x, ld_x, nrows, width, gamma, beta, stats, eps, slope, y, ld_y);
+  HL_LAUNCH_CHECK("bn_apply_kernel");
+  return HL_OK;
+}
+
+extern "C" int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64_t ld_y,
+                             const float* dy, int64_t ld_dy, int32_t nrows, int32_t width,
+                             const float* gamma, const float* stats, float eps, float slope,
+                             float* dx, int64_t ld_dx, float* dgamma, float* dbeta,
+                             void* workspace, size_t workspace_bytes, hl_stream_t stream) {
+  using namespace hl;
+  if (nrows < 1 || width < 1 || !x || !y || !dy || !dx || !stats) return HL_ERR_INVALID;
+  if (!workspace || workspace_bytes < hl_bn_workspace(nrows, width)) return HL_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  const int nblk = bn_row_blocks(nrows);
+  double* partial = reinterpret_cast<double*>(workspace);
+  float* sums = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) +
+                                         align_up((size_t)nblk * 2 * (size_t)width * sizeof(double), 256));
+  int V = vec_for(x, ld_x, width, 4);
+  V = min(V, vec_for(y, ld_y, width, V));
+  V = min(V, vec_for(dy, ld_dy, width, V));
+  V = min(V, vec_for(dx, ld_dx, width, V));
+  dim3 grid(nblk, (width + 32 * V - 1) / (32 * V));
+  if (V == 4) bn_bwd_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, width, stats, eps, slope, partial);
+  else if (V == 2) bn_bwd_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, width, stats, eps, slope, partial);
+  else bn_bwd_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, width, stats, eps, slope, partial);
+  HL_LAUNCH_CHECK("bn_bwd_partial_kernel");
+  bn_bwd_final_kernel<<<(width + 127) / 128, 128, 0, st>>>(partial, nblk, width, sums, dgamma, dbeta);
+  HL_LAUNCH_CHECK("bn_bwd_final_kernel");
+  const int g = ew_grid((int64_t)nrows * (width / V));
+  if (V == 4) bn_bwd_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, width, gamma, stats, sums, eps, slope, dx, ld_dx);
+  else if (V == 2) bn_bwd_apply_kernel<2><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, width, gamma, stats, sums, eps, slope, dx, ld_dx);
+  else bn_bwd_apply_kernel<1><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, width, gamma, stats, sums, eps, slope, dx, ld_dx);
+  HL_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  return HL_OK;
+}

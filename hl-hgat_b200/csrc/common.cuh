@@ -1,0 +1,98 @@
+// Shared helpers for libhlhgat (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "hlhgat.h"
+
+namespace hl {
+
+extern thread_local char g_last_error[256];
+int record_cuda_error(cudaError_t e, const char* where);
+
+#define HL_CUDA_CHECK(expr)                                         \
+  do {                                                              \
+    cudaError_t _e = (expr);                                        \
+    if (_e != cudaSuccess) return hl::record_cuda_error(_e, #expr); \
+  } while (0)
+
+#define HL_LAUNCH_CHECK(name)                                      \
+  do {                                                             \
+    cudaError_t _e = cudaGetLastError();                           \
+    if (_e != cudaSuccess) return hl::record_cuda_error(_e, name); \
+  } while (0)
+
+static inline cudaStream_t as_stream(hl_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// widest vector (in floats) usable for a [rows, width] slice with leading dimension ld
+static inline int vec_for(const void* p, int64_t ld, int32_t width, int want) {
+  if (p == nullptr) return want;
+  int v = want;
+  while (v > 1 && (width % v != 0 || ld % v != 0 || !aligned_to(p, sizeof(float) * v))) v >>= 1;
+  return v;
+}
+
+template <int V> struct VecT;
+template <> struct VecT<1> { using type = float; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<4> { using type = float4; };
+
+template <int V>
+struct Pack {
+  float v[V];
+};
+
+template <int V>
+__device__ __forceinline__ Pack<V> ld_pack(const float* p) {
+  Pack<V> r;
+  if constexpr (V == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else if constexpr (V == 2) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    r.v[0] = t.x; r.v[1] = t.y;
+  } else {
+    r.v[0] = __ldg(p);
+  }
+  return r;
+}
+
+// plain (coherent) load: for operands that may alias the output buffer
+template <int V>
+__device__ __forceinline__ Pack<V> ld_pack_coherent(const float* p) {
+  Pack<V> r;
+  if constexpr (V == 4) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else if constexpr (V == 2) {
+    float2 t = *reinterpret_cast<const float2*>(p);
+    r.v[0] = t.x; r.v[1] = t.y;
+  } else {
+    r.v[0] = *p;
+  }
+  return r;
+}
+
+template <int V>
+__device__ __forceinline__ void st_pack(float* p, const Pack<V>& r) {
+  if constexpr (V == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  } else if constexpr (V == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(r.v[0], r.v[1]);
+  } else {
+    *p = r.v[0];
+  }
+}
+
+// lanes per row group: smallest power of two >= ceil(width / V), capped at 32
+static inline int group_lanes(int32_t width, int v) {
+  int chunks = (width + v - 1) / v;
+  int g = 1;
+  while (g < chunks && g < 32) g <<= 1;
+  return g;
+}
+
+}  // namespace hl

@@ -1,0 +1,335 @@
+"""Differentiable host-side wrappers (torch.autograd.Function) over the C ABI.
+
+Forward and backward both run hand-written sm_100a kernels from libhlhgat.so; the only library
+calls are the dense Theta / MLP GEMMs (cuBLAS through torch.mm), as DESIGN.md states.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _native as N
+from .simplex import CsrOperator, Incidence, csr_from_coo
+
+_FAMILY = {"laguerre": N.HL_LAGUERRE, "cheb": N.HL_CHEB}
+
+
+def _side(csr, nrows, x=None, ld_x=0, t=None, ld_t=0, t_stride=0, g0=None, ld_g0=0):
+    s = N.ConvSide()
+    s.rowptr, s.colidx, s.vals = csr[0].data_ptr(), csr[1].data_ptr(), csr[2].data_ptr()
+    s.nrows = nrows
+    s.x, s.ld_x = N.ptr(x), ld_x
+    s.t, s.ld_t, s.t_stride = N.ptr(t), ld_t, t_stride
+    s.g0, s.ld_g0 = N.ptr(g0), ld_g0
+    return s
+
+
+def poly_basis_fwd(family, K, ops, xs, width):
+    """T_1..T_{K-1} for several operators in K-1 shared launches.  Returns stacked [K-1,R,width]."""
+    L = N.lib()
+    sides = (N.ConvSide * len(ops))()
+    outs = []
+    for i, (op, x) in enumerate(zip(ops, xs)):
+        x2, ldx = N.row_major(x)
+        t = torch.empty((max(K - 1, 0), op.nrows, width), dtype=torch.float32, device=x.device)
+        outs.append(t)
+        sides[i] = _side(op.fwd, op.nrows, x=x2, ld_x=ldx, t=t, ld_t=width, t_stride=op.nrows * width)
+    if K > 1:
+        N.check(L.hl_poly_basis_fwd(family, K, sides, len(ops), width, N.stream_ptr()), "hl_poly_basis_fwd")
+    return outs
+
+
+def poly_basis_bwd(family, K, ops, g0s, gts, width):
+    L = N.lib()
+    sides = (N.ConvSide * len(ops))()
+    for i, (op, g0, gt) in enumerate(zip(ops, g0s, gts)):
+        sides[i] = _side(op.bwd, op.nrows, t=gt, ld_t=width, t_stride=op.nrows * width, g0=g0, ld_g0=width)
+    if K > 1:
+        N.check(L.hl_poly_basis_bwd(family, K, sides, len(ops), width, N.stream_ptr()), "hl_poly_basis_bwd")
+
+
+class _PolyConv(torch.autograd.Function):
+    """out = sum_k T_k(x) W_k^T + b for one operator (lib/Hodge_Cheb_Conv.py:480-515 / :394-439).
+    x is [R, width] (already flattened), inner = last-dim size the Linear layers act on."""
+
+    @staticmethod
+    def forward(ctx, x, bias, op, family, inner, *weights):
+        N.require_cuda_f32(x, bias, *weights)
+        K = len(weights)
+        x = x.contiguous()
+        R, width = x.shape
+        (t,) = poly_basis_fwd(family, K, [op], [x], width)
+        xv = x.view(-1, inner)
+        w0 = weights[0]
+        out = torch.addmm(bias, xv, w0.t()) if bias is not None else torch.mm(xv, w0.t())
+        for k in range(1, K):
+            out.addmm_(t[k - 1].view(-1, inner), weights[k].t())
+        ctx.op, ctx.family, ctx.inner, ctx.has_bias = op, family, inner, bias is not None
+        ctx.save_for_backward(x, t, *weights)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, t, *weights = ctx.saved_tensors
+        K, inner, op = len(weights), ctx.inner, ctx.op
+        R, width = x.shape
+        g = g.contiguous()
+        need_x = ctx.needs_input_grad[0]
+        gx = None
+        if need_x:
+            g0 = torch.mm(g, weights[0]).view(R, width)
+            gt = torch.empty((max(K - 1, 0), R, width), dtype=torch.float32, device=x.device)
+            for k in range(1, K):
+                torch.mm(g, weights[k], out=gt[k - 1].view(-1, inner))
+            poly_basis_bwd(ctx.family, K, [op], [g0], [gt], width)
+            gx = g0
+        gws = []
+        for k in range(K):
+            if ctx.needs_input_grad[5 + k]:
+                src = x if k == 0 else t[k - 1]
+                gws.append(torch.mm(g.t(), src.view(-1, inner)))
+            else:
+                gws.append(None)
+        gb = g.sum(0) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
+        return (gx, gb, None, None, None, *gws)
+
+
+def poly_conv(x, weights, bias, op, family="laguerre"):
+    """x: [R,C] or [R,T,C]; weights: list of K [Fout,C] tensors; returns [R,Fout] / [R,T,Fout]."""
+    shp = x.shape
+    inner = shp[-1]
+    out = _PolyConv.apply(x.reshape(shp[0], -1), bias, op, _FAMILY[family], inner, *weights)
+    return out.view(*shp[:-1], -1)
+
+
+# ---------------------------------------------------------------------------------------------
+# single SpMM launches (used by the DEMO HodgeLaguerreFastConv quirk path)
+# ---------------------------------------------------------------------------------------------
+def poly_spmm(csr, nrows, xg, epi, c=(0.0, 0.0, 0.0, 0.0), p1=None, p2=None, p3=None, out=None):
+    L = N.lib()
+    xg, ldx = N.row_major(xg)
+    width = xg.shape[1]
+    if out is None:
+        out = torch.empty((nrows, width), dtype=torch.float32, device=xg.device)
+    P = (N.SpmmProblem * 1)()
+    P[0].rowptr, P[0].colidx, P[0].vals, P[0].nrows = csr[0].data_ptr(), csr[1].data_ptr(), csr[2].data_ptr(), nrows
+    P[0].xg, P[0].ld_xg = xg.data_ptr(), ldx
+    for name, t in (("p1", p1), ("p2", p2), ("p3", p3)):
+        if t is not None:
+            t2, ld = N.row_major(t)
+            setattr(P[0], name, t2.data_ptr())
+            setattr(P[0], "ld_" + name, ld)
+    P[0].out, P[0].ld_out = out.data_ptr(), out.stride(0)
+    cc = (C.c_float * 4)(*c)
+    N.check(L.hl_poly_spmm(P, 1, width, epi, cc, N.stream_ptr()), "hl_poly_spmm")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# node <-> edge simplex transfer
+# ---------------------------------------------------------------------------------------------
+def _segment_reduce(rowptr, colidx, nrows, src, post, row_scale=None, cscale=1.0, src_scale=None, out=None):
+    L = N.lib()
+    src, ld = N.row_major(src)
+    width = src.shape[1]
+    if out is None:
+        out = torch.empty((nrows, width), dtype=torch.float32, device=src.device)
+    N.check(L.hl_segment_reduce(rowptr.data_ptr(), N.ptr(colidx), nrows, src.data_ptr(), ld, N.ptr(src_scale),
+                                out.data_ptr(), out.stride(0), width, post, N.ptr(row_scale), cscale,
+                                N.stream_ptr()), "hl_segment_reduce")
+    return out
+
+
+def _endpoint_gather(inc, src, node_rcp, cscale, out=None):
+    L = N.lib()
+    src, ld = N.row_major(src)
+    width = src.shape[1]
+    if out is None:
+        out = torch.empty((inc.num_edges, width), dtype=torch.float32, device=src.device)
+    N.check(L.hl_endpoint_gather(inc.tail.data_ptr(), inc.head.data_ptr(), inc.num_edges, src.data_ptr(), ld,
+                                 N.ptr(node_rcp), out.data_ptr(), out.stride(0), width, cscale, N.stream_ptr()),
+            "hl_endpoint_gather")
+    return out
+
+
+class _EdgeToNode(torch.autograd.Function):
+    """x_s2t = (1/D) * (|B1| x_s)   (lib/Hodge_Cheb_Conv.py:294)."""
+
+    @staticmethod
+    def forward(ctx, x_s, D, inc):
+        N.require_cuda_f32(x_s, D)
+        ctx.inc = inc
+        ctx.save_for_backward(D)
+        return _segment_reduce(inc.rowptr, inc.edge, inc.num_nodes, x_s, N.HL_POST_RCP_ROW, row_scale=D)
+
+    @staticmethod
+    def backward(ctx, g):
+        (D,) = ctx.saved_tensors
+        return _endpoint_gather(ctx.inc, g, D, 1.0), None, None
+
+
+class _NodeToEdge(torch.autograd.Function):
+    """x_t2s = (|B1|^T x_t) / 2   (lib/Hodge_Cheb_Conv.py:295)."""
+
+    @staticmethod
+    def forward(ctx, x_t, inc):
+        N.require_cuda_f32(x_t)
+        ctx.inc = inc
+        return _endpoint_gather(inc, x_t, None, 0.5)
+
+    @staticmethod
+    def backward(ctx, g):
+        inc = ctx.inc
+        return _segment_reduce(inc.rowptr, inc.edge, inc.num_nodes, g, N.HL_POST_CONST, cscale=0.5), None
+
+
+def edge_to_node(x_s, D, inc):
+    return _EdgeToNode.apply(x_s, D.contiguous(), inc)
+
+
+def node_to_edge(x_t, inc):
+    return _NodeToEdge.apply(x_t, inc)
+
+
+# ---------------------------------------------------------------------------------------------
+# attention gate, cluster pooling, per-graph readout
+# ---------------------------------------------------------------------------------------------
+class _AttGate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qc, qs, k, lam, sigma):
+        N.require_cuda_f32(qc, qs, k)
+        qc, qs, k = qc.contiguous(), qs.contiguous(), k.contiguous()
+        R, dk = k.shape
+        a = torch.empty((R, 1), dtype=torch.float32, device=k.device)
+        N.check(N.lib().hl_att_gate_fwd(qc.data_ptr(), qs.data_ptr(), k.data_ptr(), R, dk, lam, sigma,
+                                        a.data_ptr(), N.stream_ptr()), "hl_att_gate_fwd")
+        ctx.lam, ctx.sigma = lam, sigma
+        ctx.save_for_backward(qc, qs, k, a)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        qc, qs, k, a = ctx.saved_tensors
+        R, dk = k.shape
+        dqc, dqs, dkk = torch.empty_like(qc), torch.empty_like(qs), torch.empty_like(k)
+        N.check(N.lib().hl_att_gate_bwd(qc.data_ptr(), qs.data_ptr(), k.data_ptr(), a.data_ptr(),
+                                        da.contiguous().data_ptr(), R, dk, ctx.lam, ctx.sigma,
+                                        dqc.data_ptr(), dqs.data_ptr(), dkk.data_ptr(), N.stream_ptr()),
+                "hl_att_gate_bwd")
+        return dqc, dqs, dkk, None, None
+
+
+def att_gate(q_cross, q_self, k, lam, sigma="sigmoid"):
+    """sigma(((1-lam) <q_cross,k> + lam <q_self,k>)/sqrt(dk))   (lib/Hodge_Cheb_Conv.py:299-304)."""
+    code = {"sigmoid": N.HL_SIGMA_SIGMOID, "relu": N.HL_SIGMA_RELU}[sigma]
+    return _AttGate.apply(q_cross, q_self, k, float(lam), code)
+
+
+class Segments:
+    """Bucketing of source rows into output rows for a mean reduction: cluster ids (int64 or the
+    reference's float ids with +inf = dropped) or contiguous per-graph counts."""
+
+    def __init__(self, rowptr, members, owner, nrows, nsrc):
+        self.rowptr, self.members, self.owner, self.nrows, self.nsrc = rowptr, members, owner, nrows, nsrc
+        cnt = (rowptr[1:] - rowptr[:-1]).clamp(min=1).to(torch.float32)
+        self.inv_count = 1.0 / cnt
+
+    @classmethod
+    def from_index(cls, index, nrows=None):
+        idx = index.reshape(-1)
+        is_float = idx.dtype.is_floating_point
+        if nrows is None:
+            finite = idx[torch.isfinite(idx)] if is_float else idx
+            nrows = int(finite.max().item()) + 1 if finite.numel() else 0
+        if is_float:
+            idx = idx.to(torch.float32)
+            owner = torch.where(torch.isfinite(idx), idx, torch.full_like(idx, -1.0)).to(torch.int32)
+        else:
+            idx = idx.to(torch.int64)
+            owner = idx.to(torch.int32)
+        rowptr, members, _, _ = csr_from_coo(idx, None, None, nrows, tie=N.HL_TIE_POSITION, row_is_float=is_float)
+        return cls(rowptr, members, owner, nrows, idx.numel())
+
+    @classmethod
+    def from_counts(cls, counts):
+        """Contiguous segments (sorted `batch` vector): counts[g] rows per graph."""
+        counts = counts.to(torch.int64)
+        ptr = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=counts.device)
+        ptr[1:] = torch.cumsum(counts, 0)
+        owner = torch.repeat_interleave(torch.arange(counts.numel(), device=counts.device, dtype=torch.int32), counts)
+        return cls(ptr, None, owner, counts.numel(), int(owner.numel()))
+
+
+class _SegmentMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, scale, seg):
+        N.require_cuda_f32(src, scale)
+        src = src.contiguous()
+        sc = None if scale is None else scale.reshape(-1).contiguous()
+        ctx.seg = seg
+        ctx.save_for_backward(src, sc)
+        return _segment_reduce(seg.rowptr, seg.members, seg.nrows, src, N.HL_POST_MEAN, src_scale=sc)
+
+    @staticmethod
+    def backward(ctx, g):
+        src, sc = ctx.saved_tensors
+        seg = ctx.seg
+        g = g.contiguous()
+        dsrc = torch.empty_like(src)
+        dsc = torch.empty(src.shape[0], dtype=torch.float32, device=src.device) if sc is not None else None
+        N.check(N.lib().hl_owner_gather(seg.owner.data_ptr(), src.shape[0], g.data_ptr(), g.stride(0),
+                                        seg.inv_count.data_ptr(), N.ptr(sc), src.data_ptr(), src.stride(0),
+                                        dsrc.data_ptr(), dsrc.stride(0), N.ptr(dsc), src.shape[1], N.stream_ptr()),
+                "hl_owner_gather")
+        return dsrc, (None if dsc is None else dsc.view(-1, 1)), None
+
+
+def segment_mean(src, seg, scale=None):
+    """mean over each bucket of (scale[m] * src[m]) -- scatter_mean / global_mean_pool with the gate
+    multiply fused (lib/Hodge_ST_Model.py:141-150, :636)."""
+    return _SegmentMean.apply(src, scale, seg)
+
+
+# ---------------------------------------------------------------------------------------------
+# BatchNorm (training statistics) + activation, optionally writing into a slice of a wide buffer
+# ---------------------------------------------------------------------------------------------
+class _BnAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, slope):
+        N.require_cuda_f32(x, gamma, beta)
+        L = N.lib()
+        x, ldx = N.row_major(x)
+        R, F = x.shape
+        y = torch.empty((R, F), dtype=torch.float32, device=x.device)
+        stats = torch.empty(2 * F, dtype=torch.float32, device=x.device)
+        nb = L.hl_bn_workspace(R, F)
+        ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+        N.check(L.hl_bn_act_fwd(x.data_ptr(), ldx, R, F, N.ptr(gamma), N.ptr(beta), eps, slope,
+                                y.data_ptr(), y.stride(0), stats.data_ptr(), ws.data_ptr(), nb, N.stream_ptr()),
+                "hl_bn_act_fwd")
+        ctx.eps, ctx.slope = eps, slope
+        ctx.save_for_backward(x, y, gamma, stats)
+        ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _):
+        x, y, gamma, stats = ctx.saved_tensors
+        L = N.lib()
+        R, F = x.shape
+        dy, lddy = N.row_major(dy)
+        dx = torch.empty((R, F), dtype=torch.float32, device=x.device)
+        dgamma = torch.empty(F, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(F, dtype=torch.float32, device=x.device)
+        nb = L.hl_bn_workspace(R, F)
+        ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+        N.check(L.hl_bn_act_bwd(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), dy.data_ptr(), lddy, R, F,
+                                N.ptr(gamma), stats.data_ptr(), ctx.eps, ctx.slope, dx.data_ptr(), dx.stride(0),
+                                dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), nb, N.stream_ptr()),
+                "hl_bn_act_bwd")
+        return dx, dgamma, dbeta, None, None
+
+
+def bn_act_train(x, gamma, beta, eps=1e-5, slope=0.0):
+    """Training-mode BatchNorm1d over rows + (leaky) ReLU; returns (y, stats[2F] = mean | biased var)."""
+    return _BnAct.apply(x, gamma, beta, float(eps), float(slope))

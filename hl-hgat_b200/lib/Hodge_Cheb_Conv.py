@@ -1,0 +1,355 @@
+"""B200-native operator layer behind the reference's module API (lib/Hodge_Cheb_Conv.py).
+
+Same class names, constructor arguments, attribute / state_dict names and forward signatures
+as the reference; the arithmetic runs in libhlhgat.so (sm_100a) -- CUDA tensors only, no
+PyG / torch_scatter / torch_sparse, no CPU fallback.
+"""
+import math
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+from torch.nn import Parameter
+
+from .. import functional as F_hl
+from .. import _native as N
+from ..simplex import operator_for, incidence_for, CsrOperator, Incidence
+
+__all__ = ["HodgeLaguerreConv", "HodgeChebConv", "HodgeLaguerreFastConv", "NodeEdgeInt", "MSI",
+           "SAPool", "HL_filter", "GraphBatchNorm", "NEConv", "adj2par1", "degree"]
+
+
+class _GlorotLinear(nn.Module):
+    """Stand-in for PyG's dense Linear(bias=False, weight_initializer='glorot'): one `weight`
+    [out, in] parameter (state_dict key `lins.{k}.weight`)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight = Parameter(torch.empty(out_channels, in_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        a = math.sqrt(6.0 / (self.in_channels + self.out_channels))
+        with torch.no_grad():
+            self.weight.uniform_(-a, a)
+
+    def forward(self, x):
+        return torch.matmul(x, self.weight.t())
+
+
+class _HodgePolyConv(nn.Module):
+    family = None
+
+    def __init__(self, in_channels: int, out_channels: int, K: int, bias: bool = True, **kwargs):
+        super().__init__()
+        assert K > 0
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.lins = nn.ModuleList([_GlorotLinear(in_channels, out_channels) for _ in range(K)])
+        if bias:
+            self.bias = Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for lin in self.lins:
+            lin.reset_parameters()
+        if self.bias is not None:
+            with torch.no_grad():
+                self.bias.zero_()
+
+    def forward(self, x: Tensor, edge_index, edge_weight=None, batch=None):
+        """`edge_index` is the reference's int64 COO [2,nnz] (bucketed once per batch and cached) or
+        an already built `CsrOperator`.  `batch` is ignored, as in the reference."""
+        op = edge_index if isinstance(edge_index, CsrOperator) else operator_for(edge_index, edge_weight, x.shape[0])
+        return F_hl.poly_conv(x, [lin.weight for lin in self.lins], self.bias, op, self.family)
+
+    def __repr__(self) -> str:
+        return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels}, K={len(self.lins)})"
+
+
+class HodgeLaguerreConv(_HodgePolyConv):
+    """Reference lib/Hodge_Cheb_Conv.py:452-523."""
+    family = "laguerre"
+
+
+class HodgeChebConv(_HodgePolyConv):
+    """Reference lib/Hodge_Cheb_Conv.py:366-448.  (The reference's 3-D path raises at :411 and its
+    __repr__ raises at :448; here 3-D input is flattened like the Laguerre conv -- A(.) acts on
+    columns independently, so the intended result does not depend on the flattening order.)"""
+    family = "cheb"
+
+
+class HodgeLaguerreFastConv(_HodgePolyConv):
+    """HL-HGAT-DEMO/lib/Hodge_Cheb_Conv.py:519-582: forward(x, adj_t).  `adj_t` is a CsrOperator or an
+    `(edge_index, edge_weight)` pair.  quirk=True reproduces DEMO :561 (every order k >= 2 propagates
+    the ORIGINAL x); quirk=False is the HodgeLaguerreConv polynomial."""
+    family = "laguerre"
+
+    def __init__(self, in_channels, out_channels, K, bias=True, quirk=True, **kwargs):
+        super().__init__(in_channels, out_channels, K, bias)
+        self.quirk = quirk
+
+    def forward(self, x, adj_t):
+        op = adj_t if isinstance(adj_t, CsrOperator) else operator_for(adj_t[0], adj_t[1], x.shape[0])
+        ws = [lin.weight for lin in self.lins]
+        if not self.quirk or len(ws) < 3:
+            return F_hl.poly_conv(x, ws, self.bias, op, "laguerre")
+        return _fastconv_quirk(x, ws, self.bias, op)
+
+
+class _QuirkBasis(torch.autograd.Function):
+    """T_1 = x - A x, T_{k+1} = (-A x + (2k+1) T_k - k T_{k-1})/(k+1): one SpMM, the rest elementwise
+    inside the SpMM epilogues (xg = x for every order)."""
+
+    @staticmethod
+    def forward(ctx, x, op, K):
+        x = x.contiguous()
+        ts = [x]
+        for k in range(K - 1):
+            if k == 0:
+                ts.append(F_hl.poly_spmm(op.fwd, op.nrows, x, N.HL_EPI_LAGUERRE_FIRST, p1=x))
+            else:
+                ts.append(F_hl.poly_spmm(op.fwd, op.nrows, x, N.HL_EPI_LAGUERRE_STEP, c=(float(k), 0, 0, 0),
+                                         p1=ts[k], p2=ts[k - 1]))
+        ctx.op, ctx.K = op, K
+        return tuple(ts[1:])
+
+    @staticmethod
+    def backward(ctx, *gs):
+        K, op = ctx.K, ctx.op
+        # S_k (k>=1) = G_k + b_k S_{k+1} + c_{k+1} S_{k+2};  dx = b_0 S_1 + c_1 S_2 + A^T sum_k a_k S_{k+1}
+        S = [None] * (K + 2)
+        acc = None
+        for k in range(K - 1, 0, -1):
+            s = gs[k - 1].clone()
+            if S[k + 1] is not None:
+                s = s + (2.0 * k + 1.0) / (k + 1) * S[k + 1]
+            if S[k + 2] is not None:
+                s = s - (k + 1.0) / (k + 2) * S[k + 2]
+            S[k] = s
+            a = -1.0 if k == 1 else -1.0 / k          # a_{k-1}
+            acc = a * s if acc is None else acc + a * s
+        own = S[1].clone()
+        if S[2] is not None:
+            own = own - 0.5 * S[2]
+        dx = F_hl.poly_spmm(op.bwd, op.nrows, acc.contiguous(), N.HL_EPI_LINCOMB, c=(1.0, 1.0, 0, 0), p1=own)
+        return dx, None, None
+
+
+def _fastconv_quirk(x, ws, bias, op):
+    shp = x.shape
+    xf = x.reshape(shp[0], -1)
+    ts = _QuirkBasis.apply(xf, op, len(ws))
+    out = torch.matmul(x, ws[0].t())
+    for k in range(1, len(ws)):
+        out = out + torch.matmul(ts[k - 1].view(shp), ws[k].t())
+    return out + bias if bias is not None else out
+
+
+# ---------------------------------------------------------------------------------------------
+def adj2par1(edge_index, num_node, num_edge):
+    """Reference lib/Hodge_Dataset.py:169-191: B1 as a sparse COO float tensor [N,E], -1 at the tail
+    (edge_index[0]), +1 at the head.  The int32 incidence tables the kernels use are built once and
+    attached to the returned tensor (`._hl_incidence`)."""
+    e = edge_index.shape[1]
+    ar = torch.arange(e, device=edge_index.device)
+    idx = torch.stack([torch.cat([edge_index[0], edge_index[1]]), torch.cat([ar, ar])])
+    val = torch.cat([edge_index.new_full((e,), -1), edge_index.new_full((e,), 1)]).to(torch.float)
+    par = torch.sparse_coo_tensor(idx, val, (num_node, num_edge), check_invariants=False)
+    if edge_index.is_cuda:
+        par._hl_incidence = incidence_for(edge_index, num_node)
+    return par
+
+
+def degree(index, num_nodes=None, dtype=torch.float32):
+    """PyG utils.degree (used as `degree(edge_index.view(-1)) [+ 1e-6]`, lib/Hodge_ST_Model.py:624)."""
+    n = int(index.max()) + 1 if num_nodes is None else int(num_nodes)
+    out = torch.zeros(n, dtype=dtype, device=index.device)
+    return out.scatter_add_(0, index, torch.ones(index.numel(), dtype=dtype, device=index.device))
+
+
+def _incidence_of(par):
+    if isinstance(par, Incidence):
+        return par
+    inc = getattr(par, "_hl_incidence", None)
+    if inc is not None:
+        return inc
+    # a foreign sparse +-1 matrix: recover (tail, head) per column; cached on the tensor
+    pc = par.coalesce()
+    idx, val = pc.indices(), pc.values()
+    order = torch.argsort(idx[1] * 2 + (val > 0).long(), stable=True)
+    rows = idx[0][order].view(-1, 2).t().contiguous()
+    inc = incidence_for(rows, par.shape[0])
+    par._hl_incidence = inc
+    return inc
+
+
+class NodeEdgeInt(nn.Module):
+    """Reference lib/Hodge_Cheb_Conv.py:255-309 (MSI :61-115 is the same module)."""
+
+    def __init__(self, d=64, dk=32, dv=64, dl=64, only_att=False, sigma=nn.Sigmoid(), l=0.9):
+        super().__init__()
+        dl = dv
+        self.sigma = sigma
+        self.dk = dk
+        self.only_att = only_att
+        if only_att:
+            self.WQ_Node = nn.Linear(d, dk)
+            self.WK_Node = nn.Linear(d, dk)
+            self.WQ_Edge = nn.Linear(d, dk)
+            self.WK_Edge = nn.Linear(d, dk)
+        else:
+            self.WV_Node = nn.Sequential(nn.Linear(d * 2, dl), nn.BatchNorm1d(dl), nn.ReLU(),
+                                         nn.Linear(dl, dv), nn.BatchNorm1d(dv), nn.ReLU())
+            self.WV_Edge = nn.Sequential(nn.Linear(d * 2, dl), nn.BatchNorm1d(dl), nn.ReLU(),
+                                         nn.Linear(dl, dv), nn.BatchNorm1d(dv), nn.ReLU())
+        self.lambda_Node = l
+        self.lambda_Edge = l
+
+    def _sigma_name(self):
+        if isinstance(self.sigma, nn.Sigmoid):
+            return "sigmoid"
+        if isinstance(self.sigma, nn.ReLU):
+            return "relu"
+        return None
+
+    def forward(self, x_t, x_s, par, D):
+        inc = _incidence_of(par)
+        x_s2t = F_hl.edge_to_node(x_s, D, inc)
+        x_t2s = F_hl.node_to_edge(x_t, inc)
+        if self.only_att:
+            k_t, k_s = self.WK_Node(x_t), self.WK_Edge(x_s)
+            name = self._sigma_name()
+            if name is None:        # arbitrary activation object: gate pre-activation through the kernel is not available
+                raise N.HlError("NodeEdgeInt(only_att=True) supports sigma = nn.Sigmoid() or nn.ReLU()")
+            a_t = F_hl.att_gate(self.WQ_Edge(x_s2t), self.WQ_Node(x_t), k_t, self.lambda_Node, name)
+            a_s = F_hl.att_gate(self.WQ_Node(x_t2s), self.WQ_Edge(x_s), k_s, self.lambda_Edge, name)
+            return a_t, a_s
+        x_t1 = _mlp(self.WV_Node, x_s2t, x_t)
+        x_s1 = _mlp(self.WV_Edge, x_t2s, x_s)
+        return x_t1, x_s1
+
+
+MSI = NodeEdgeInt
+
+
+def _bn_relu(bn, x, slope=0.0):
+    """nn.BatchNorm1d (+ReLU) through the fused kernels in training mode; running statistics updated
+    exactly like torch (momentum, unbiased variance)."""
+    if not (bn.training or not bn.track_running_stats):
+        y = torch.nn.functional.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
+        return torch.nn.functional.leaky_relu(y, slope) if slope != 1.0 else y
+    y, stats = F_hl.bn_act_train(x, bn.weight, bn.bias, bn.eps, slope)
+    if bn.track_running_stats and bn.training:
+        with torch.no_grad():
+            f = x.shape[1]
+            n = x.shape[0]
+            bn.num_batches_tracked += 1
+            m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            bn.running_mean.mul_(1 - m).add_(stats[:f], alpha=m)
+            bn.running_var.mul_(1 - m).add_(stats[f:], alpha=m * n / max(n - 1, 1))
+    return y
+
+
+def _mlp(seq, transferred, own):
+    """Linear(cat[transferred, own]) -> BN -> ReLU -> Linear -> BN -> ReLU without materialising the
+    concat: the first Linear is split over its two column blocks (lib/Hodge_Cheb_Conv.py:307-308)."""
+    lin0, bn0, _, lin1, bn1, _ = seq
+    d = transferred.shape[1]
+    h = torch.addmm(lin0.bias, transferred, lin0.weight[:, :d].t())
+    h = h.addmm(own, lin0.weight[:, d:].t())
+    h = _bn_relu(bn0, h)
+    h = torch.addmm(lin1.bias, h, lin1.weight.t())
+    return _bn_relu(bn1, h)
+
+
+class GraphBatchNorm(nn.Module):
+    """gnn.BatchNorm: a wrapper whose only child is `.module = nn.BatchNorm1d` (state_dict keys
+    `module.weight`, ...).  `forward_act` fuses the following (leaky) ReLU."""
+
+    def __init__(self, in_channels, eps=1e-5, momentum=0.1):
+        super().__init__()
+        self.module = nn.BatchNorm1d(in_channels, eps, momentum)
+
+    def forward(self, x):
+        return _bn_relu(self.module, x, slope=1.0)
+
+    def forward_act(self, x, slope=0.0):
+        return _bn_relu(self.module, x, slope=slope)
+
+
+class NEConv(nn.Module):
+    """The reference's 9-entry gnn.Sequential NEConv block (lib/Hodge_ST_Model.py:578-590,
+    lib/Hodge_Cheb_Conv.py:142-154): conv_t, BN, act, dropout, conv_s, BN, act, dropout, list-pack.
+    Children keep the reference's names module_0 / module_1 / module_4 / module_5."""
+
+    def __init__(self, fin_t, fin_s, fout, K, dropout_ratio=0.0, slope=0.0, conv=HodgeLaguerreConv):
+        super().__init__()
+        self.module_0 = conv(fin_t, fout, K=K)
+        self.module_1 = GraphBatchNorm(fout)
+        self.module_4 = conv(fin_s, fout, K=K)
+        self.module_5 = GraphBatchNorm(fout)
+        self.slope, self.p = slope, dropout_ratio
+
+    def forward(self, x_t, edge_index_t, edge_weight_t, x_s, edge_index_s, edge_weight_s):
+        x_t = self.module_1.forward_act(self.module_0(x_t, edge_index_t, edge_weight_t), self.slope)
+        x_s = self.module_5.forward_act(self.module_4(x_s, edge_index_s, edge_weight_s), self.slope)
+        if self.p > 0.0:
+            x_t = torch.nn.functional.dropout(x_t, self.p, self.training)
+            x_s = torch.nn.functional.dropout(x_s, self.p, self.training)
+        return [x_t, x_s]
+
+
+class HL_filter(nn.Module):
+    """Reference lib/Hodge_Cheb_Conv.py:117-188."""
+
+    def __init__(self, channels=2, filters=32, K=4, node_dim=64, edge_dim=64, dropout_ratio=0.0,
+                 leaky_slope=0.1, if_dense=True):
+        super().__init__()
+        self.channels, self.filters = channels, filters
+        self.node_dim, self.edge_dim, self.if_dense = node_dim, edge_dim, if_dense
+        t_in, s_in = node_dim, edge_dim
+        for j in range(channels):
+            if if_dense:
+                setattr(self, f"MSI{j}", MSI(d=t_in, dv=filters))
+                setattr(self, f"NEConv{j}", NEConv(filters, filters, filters, K, dropout_ratio, leaky_slope))
+                t_in, s_in = t_in + filters, s_in + filters
+            else:
+                setattr(self, f"NEConv{j}", NEConv(t_in, s_in, filters, K, dropout_ratio, leaky_slope))
+                t_in, s_in = filters, filters
+
+    def forward(self, x_t0, edge_index_t, edge_weight_t, x_s0, edge_index_s, edge_weight_s, par_1=None, D=None):
+        for j in range(self.channels):
+            if self.if_dense:
+                x_t, x_s = getattr(self, f"MSI{j}")(x_t0, x_s0, par_1, D)
+                x_t, x_s = getattr(self, f"NEConv{j}")(x_t, edge_index_t, edge_weight_t, x_s, edge_index_s, edge_weight_s)
+                x_t0 = torch.cat([x_t0, x_t], dim=-1)
+                x_s0 = torch.cat([x_s0, x_s], dim=-1)
+            else:
+                x_t0, x_s0 = getattr(self, f"NEConv{j}")(x_t0, edge_index_t, edge_weight_t, x_s0, edge_index_s, edge_weight_s)
+        return x_t0, x_s0
+
+
+class SAPool(nn.Module):
+    """Reference lib/Hodge_Cheb_Conv.py:36-59: gate -> cluster mean (edges with +inf id dropped) ->
+    switch to the level-(k+1) operators."""
+
+    def __init__(self, d=64, dk=32):
+        super().__init__()
+        self.NEAtt = MSI(d=d, dk=dk, only_att=True, sigma=nn.Sigmoid())
+
+    def forward(self, x_t0, x_s0, par_1, D, datas, pos_ts, pos_ss, k, device="cuda:0"):
+        att_t, att_s = self.NEAtt(x_t0, x_s0, par_1, D)
+        x_t0 = F_hl.segment_mean(x_t0, F_hl.Segments.from_index(pos_ts[k]), att_t)
+        x_s0 = F_hl.segment_mean(x_s0, F_hl.Segments.from_index(pos_ss[k]), att_s)
+        nxt = datas[k + 1]
+        edge_index_s, edge_weight_s = nxt.edge_index_s.to(device), nxt.edge_weight_s.to(device)
+        edge_index_t, edge_weight_t = nxt.edge_index_t.to(device), nxt.edge_weight_t.to(device)
+        k += 1
+        ei = datas[k].edge_index.to(device)
+        par_1 = adj2par1(ei, x_t0.shape[0], x_s0.shape[0])
+        D = degree(ei.view(-1), num_nodes=x_t0.shape[0]) + 1e-6
+        return x_t0, x_s0, par_1, D, k, edge_index_t, edge_weight_t, edge_index_s, edge_weight_s, att_t, att_s

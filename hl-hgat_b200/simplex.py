@@ -1,0 +1,130 @@
+"""Per-mini-batch device-side operator tables.
+
+The reference hands every layer an int64 COO `(edge_index, edge_weight)` (L0 / L1) and a sparse
+COO boundary matrix `par` and re-derives what it needs on every call (gather/scatter over the
+COO in `propagate`, `par.abs()` re-coalescing in `NodeEdgeInt`, lib/Hodge_Cheb_Conv.py:294-295,
+494).  Here each operator is bucketed ONCE per mini-batch into int32 CSR tables (forward and
+transpose) by `hl_csr_from_coo`, cached on the identity of the incoming tensors, and every
+layer of the model reuses them.
+"""
+import torch
+
+from . import _native as N
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+def csr_from_coo(row, col, val, nrows, tie=N.HL_TIE_POSITION, want_perm=False, row_is_float=False):
+    """Bucket COO entries by `row` (int64, or float32 cluster ids when row_is_float) on the GPU.
+    Returns (rowptr[int32, nrows+1], colidx[int32, nnz], vals[f32, nnz] | None, perm | None).
+    Entries with row outside [0, nrows) (or +inf) are dropped; the outputs keep the full nnz
+    allocation and rowptr[-1] says how many are valid."""
+    L = N.lib()
+    dev = row.device
+    if not row.is_cuda:
+        raise N.HlError("csr_from_coo needs CUDA tensors (no CPU fallback)")
+    nnz = int(row.numel())
+    row = row.contiguous()
+    if row_is_float:
+        assert row.dtype == torch.float32
+    else:
+        assert row.dtype == torch.int64
+    col_c = None if col is None else col.contiguous()
+    assert col_c is None or col_c.dtype == torch.int64
+    val_c = None if val is None else val.contiguous()
+    rowptr = torch.empty(nrows + 1, dtype=torch.int32, device=dev)
+    colidx = torch.empty(nnz, dtype=torch.int32, device=dev)
+    vals = torch.empty(nnz, dtype=torch.float32, device=dev) if val is not None else None
+    perm = torch.empty(nnz, dtype=torch.int32, device=dev) if want_perm else None
+    ws_bytes = L.hl_csr_from_coo_workspace(nnz, nrows)
+    ws = _workspace(ws_bytes, dev)
+    N.check(L.hl_csr_from_coo(None if row_is_float else row.data_ptr(), row.data_ptr() if row_is_float else None,
+                              N.ptr(col_c), N.ptr(val_c), nnz, nrows, tie,
+                              rowptr.data_ptr(), colidx.data_ptr(), N.ptr(vals), N.ptr(perm),
+                              ws.data_ptr(), ws_bytes, N.stream_ptr()), "hl_csr_from_coo")
+    return rowptr, colidx, vals, perm
+
+
+class CsrOperator:
+    """A = the propagate operator of `(edge_index, edge_weight)`: (A v)[i] = sum_{e: ei[1][e]=i}
+    w[e] v[ei[0][e]] (lib/Hodge_Cheb_Conv.py:518-519, flow source->target).  Holds CSR by target
+    row in COO order (forward) and CSR of A^T (backward), built lazily."""
+
+    def __init__(self, edge_index, edge_weight, nrows):
+        if edge_weight is None:
+            edge_weight = torch.ones(edge_index.shape[1], dtype=torch.float32, device=edge_index.device)
+        self.nrows = int(nrows)
+        self.nnz = int(edge_index.shape[1])
+        self._ei, self._ew = edge_index, edge_weight
+        self._fwd = self._bwd = None
+
+    @property
+    def fwd(self):
+        if self._fwd is None:
+            self._fwd = csr_from_coo(self._ei[1], self._ei[0], self._ew, self.nrows)[:3]
+        return self._fwd
+
+    @property
+    def bwd(self):
+        if self._bwd is None:
+            self._bwd = csr_from_coo(self._ei[0], self._ei[1], self._ew, self.nrows)[:3]
+        return self._bwd
+
+
+class Incidence:
+    """Tables of |B1| for a batch: `tail`/`head` (int32 [E], tail = edge_index[0]) and the
+    node -> incident-edge CSR in ascending edge id (the order of the coalesced `par.abs()`)."""
+
+    def __init__(self, edge_index, num_nodes):
+        ei = edge_index
+        e = int(ei.shape[1])
+        self.num_nodes, self.num_edges = int(num_nodes), e
+        self.tail = ei[0].to(torch.int32).contiguous()
+        self.head = ei[1].to(torch.int32).contiguous()
+        ar = torch.arange(e, dtype=torch.int64, device=ei.device)
+        self.rowptr, self.edge, _, _ = csr_from_coo(ei.reshape(-1), torch.cat([ar, ar]), None,
+                                                    self.num_nodes, tie=N.HL_TIE_COLUMN)
+
+    def degree(self):
+        return (self.rowptr[1:] - self.rowptr[:-1]).to(torch.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# identity-keyed caches: the unchanged reference models re-pass the same COO tensors to every
+# layer and rebuild B1 at every stage (lib/Hodge_ST_Model.py:623-624); conversion happens once.
+# ---------------------------------------------------------------------------------------------
+_OP_CACHE = {}
+_CACHE_LIMIT = 64
+
+
+def _key(*tensors):
+    return tuple((t.data_ptr(), tuple(t.shape), t._version) for t in tensors if t is not None)
+
+
+def _put(cache, key, value, keep):
+    if len(cache) >= _CACHE_LIMIT:
+        cache.pop(next(iter(cache)))
+    cache[key] = (value, keep)        # `keep` pins the source tensors so data_ptr stays unique
+    return value
+
+
+def operator_for(edge_index, edge_weight, nrows):
+    key = ("op", nrows) + _key(edge_index, edge_weight)
+    hit = _OP_CACHE.get(key)
+    if hit is not None:
+        return hit[0]
+    return _put(_OP_CACHE, key, CsrOperator(edge_index, edge_weight, nrows), (edge_index, edge_weight))
+
+
+def incidence_for(edge_index, num_nodes):
+    key = ("inc", num_nodes) + _key(edge_index)
+    hit = _OP_CACHE.get(key)
+    if hit is not None:
+        return hit[0]
+    return _put(_OP_CACHE, key, Incidence(edge_index, num_nodes), (edge_index,))
+
+
+def clear_caches():
+    _OP_CACHE.clear()

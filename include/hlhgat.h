@@ -1,0 +1,214 @@
+/*
+ * hlhgat.h -- C ABI of libhlhgat.so: the B200 (sm_100a) kernels behind the HL-HGAT hot path.
+ *
+ * The reference (deepika090/HL-HGAT) has no FFI of its own: every device kernel on this path is
+ * reached through a third-party Python call (PyG MessagePassing.propagate, torch.sparse.mm,
+ * torch_scatter.scatter_mean, ...).  Each entry point below names the reference call site(s) it
+ * replaces (paths relative to the reference root).  Conventions for every function:
+ *   - all data pointers are DEVICE pointers unless the parameter is documented as host;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises;
+ *   - no allocation inside: scratch is passed in, sized by the matching *_workspace() query;
+ *   - returns HL_OK (0) or a negative hl_status; never throws;
+ *   - matrices are row-major fp32 with an explicit leading dimension `ld` (elements), so callers
+ *     can read/write column slices of wider buffers (the dense-connection concat buffers);
+ *   - indices inside the library are int32 (the reference uses int64 COO; conversion happens
+ *     once per mini-batch in hl_csr_from_coo / hl_build_*).
+ * Thread-compatible, not thread-safe.
+ */
+#ifndef HLHGAT_H_
+#define HLHGAT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HL_ABI_VERSION 1
+
+typedef enum {
+  HL_OK = 0,
+  HL_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, unsupported mode) */
+  HL_ERR_WORKSPACE = -2,   /* workspace too small */
+  HL_ERR_CUDA = -3,        /* a CUDA runtime call / launch failed: see hl_last_cuda_error() */
+  HL_ERR_ALIGN = -4        /* pointer / leading dimension not aligned as documented */
+} hl_status;
+
+typedef void* hl_stream_t; /* cudaStream_t */
+
+int hl_version(void);
+const char* hl_status_string(int status);
+const char* hl_last_cuda_error(void);
+int hl_device_sm_count(void);
+
+/* --------------------------------------------------------------------------------------------
+ * CSR construction from a COO edge list (once per mini-batch and operator).
+ * Replaces: the implicit per-call work of PyG `propagate` (lib/Hodge_Cheb_Conv.py:494,502:
+ * index_select + scatter over an int64 COO), the `par.abs()` re-coalesce of
+ * lib/Hodge_Cheb_Conv.py:294-295, and the cluster bucketing inside torch_scatter.scatter_mean
+ * (lib/Hodge_ST_Model.py:147,150).
+ *
+ * Groups entries by `row[i]` (rows outside [0,nrows) are dropped) and orders each group by
+ *   tie == HL_TIE_POSITION : the entry's position i in the COO (the CPU reference's summation
+ *                            order for index_add_; SURVEY.md section 7 "Deterministic ordering")
+ *   tie == HL_TIE_COLUMN   : col[i] ascending (the order of a coalesced sparse tensor).
+ * Outputs: rowptr[nrows+1], colidx[nnz_kept], vals[nnz_kept] (if val != NULL),
+ *          perm[nnz_kept] = original position (if perm != NULL).  rowptr[nrows] = nnz_kept.
+ * `row_f32`: alternative float32 row ids (the reference's float cluster ids, +inf = dropped,
+ * lib/Hodge_ST_Model.py:142-144); exactly one of row / row_f32 must be non-NULL.
+ * -------------------------------------------------------------------------------------------- */
+enum { HL_TIE_POSITION = 0, HL_TIE_COLUMN = 1 };
+size_t hl_csr_from_coo_workspace(int64_t nnz, int64_t nrows);
+int hl_csr_from_coo(const int64_t* row, const float* row_f32, const int64_t* col /* NULL = position */,
+                    const float* val, int64_t nnz, int64_t nrows, int tie,
+                    int32_t* rowptr, int32_t* colidx, float* vals, int32_t* perm,
+                    void* workspace, size_t workspace_bytes, hl_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Polynomial SpMM with fused recurrence epilogue: one launch per polynomial order over one or
+ * several operators (node side L0 and edge side L1 of a NEConv block share a launch).
+ * Replaces: `self.propagate(edge_index, x=..., norm=...)` + the recurrence arithmetic,
+ * lib/Hodge_Cheb_Conv.py:494 (T1 = x - A x), :502+:507 (Laguerre step), :412-416 (Chebyshev
+ * T1), :430-432 (Chebyshev step); HL-HGAT-DEMO/lib/Hodge_Cheb_Conv.py:577-578 (CSR SpMM).
+ *
+ *   a[i,:]   = sum_{p in row i, ascending} vals[p] * xg[colidx[p], :]     (product rounded, then added:
+ *                                                                          bit-equal to the CPU reference)
+ *   out[i,:] = HL_EPI_LAGUERRE_FIRST : p1 - a
+ *              HL_EPI_LAGUERRE_STEP  : (-a + (2k+1) p1 - k p2) / (k+1)     k = (int)c[0]
+ *              HL_EPI_CHEB_FIRST     : a
+ *              HL_EPI_CHEB_STEP      : 2 a - p2
+ *              HL_EPI_LINCOMB        : c[0] a + c[1] p1 + c[2] p2 + c[3] p3  (NULL operands skipped)
+ * `width` columns; every ld and pointer must allow the widest vector that divides `width`
+ * (16 B for width % 4 == 0, 8 B for width % 2 == 0).  out may alias p1/p2/p3 (own-row only) but
+ * not xg.
+ * -------------------------------------------------------------------------------------------- */
+typedef struct {
+  const int32_t* rowptr;
+  const int32_t* colidx;
+  const float* vals;
+  int32_t nrows;
+  int32_t reserved;
+  const float* xg;  int64_t ld_xg;
+  const float* p1;  int64_t ld_p1;
+  const float* p2;  int64_t ld_p2;
+  const float* p3;  int64_t ld_p3;
+  float* out;       int64_t ld_out;
+} hl_spmm_problem;
+
+enum {
+  HL_EPI_LAGUERRE_FIRST = 0,
+  HL_EPI_LAGUERRE_STEP = 1,
+  HL_EPI_CHEB_FIRST = 2,
+  HL_EPI_CHEB_STEP = 3,
+  HL_EPI_LINCOMB = 4
+};
+#define HL_MAX_SPMM_PROBLEMS 4
+int hl_poly_spmm(const hl_spmm_problem* problems /* host */, int nproblems, int32_t width, int epilogue,
+                 const float* c /* host, 4 floats */, hl_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Whole polynomial basis of one convolution (K-1 launches of hl_poly_spmm):
+ * forward: block k-1 of t (at t + (k-1)*t_stride, leading dimension ld_t) = T_k(x), k = 1..K-1
+ *          (T_0 = x is not copied).  t_stride = width gives the column-concatenated layout
+ *          [R,(K-1)*width]; t_stride = nrows*ld_t the stacked layout [K-1,R,width].
+ * backward: given g0 = dL/dT_0-direct [R,width] and block k-1 of t = dL/dT_k-direct, runs the
+ *           adjoint recurrence in place on the TRANSPOSED operator; on return g0 holds dL/dx.
+ * Replaces: HodgeLaguerreConv.forward / HodgeChebConv.forward minus the dense Linear layers
+ * (lib/Hodge_Cheb_Conv.py:480-515, :394-439) and their autograd.
+ * family: HL_LAGUERRE / HL_CHEB.  All sides share `width` (else call once per side).
+ * -------------------------------------------------------------------------------------------- */
+enum { HL_LAGUERRE = 0, HL_CHEB = 1 };
+typedef struct {
+  const int32_t* rowptr;   /* forward: CSR by target row; backward: CSR of the transpose */
+  const int32_t* colidx;
+  const float* vals;
+  int32_t nrows;
+  int32_t reserved;
+  const float* x;  int64_t ld_x;   /* forward: input x.   backward: unused (NULL) */
+  float* t;        int64_t ld_t;   /* forward: basis out (K-1 blocks). backward: gt (in/out) */
+  int64_t t_stride;                /* elements between consecutive blocks of t */
+  float* g0;       int64_t ld_g0;  /* backward only: in dL/dT_0-direct, out dL/dx */
+} hl_conv_side;
+int hl_poly_basis_fwd(int family, int K, const hl_conv_side* sides /* host */, int nsides, int32_t width,
+                      hl_stream_t stream);
+int hl_poly_basis_bwd(int family, int K, const hl_conv_side* sides /* host */, int nsides, int32_t width,
+                      hl_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Segmented (CSR-bucketed) row reduction with deterministic ascending order.
+ *   dst[r,:] = post( sum_{p in [rowptr[r], rowptr[r+1])} pre(src[m_p, :]) ),  m_p = colidx ? colidx[p] : p
+ *   pre  : src_scale ? src_scale[m] * v : v                  (attention gate, rounded before the sum)
+ *   post : HL_POST_NONE     s
+ *          HL_POST_CONST    s * cscale
+ *          HL_POST_RCP_ROW  (1.0f / row_scale[r]) * s         (the 1/D of :294)
+ *          HL_POST_MEAN     s / max(count, 1)                 (scatter_mean / global_mean_pool)
+ * Replaces: torch.sparse.mm(par.abs(), x_s) * (1/D)  lib/Hodge_Cheb_Conv.py:294 (=:100);
+ *           its adjoint |B1| g / 2 (backward of :295); scatter_mean lib/Hodge_ST_Model.py:147,150,
+ *           lib/Hodge_Cheb_Conv.py:50,53; global_mean_pool lib/Hodge_ST_Model.py:636.
+ * -------------------------------------------------------------------------------------------- */
+enum { HL_POST_NONE = 0, HL_POST_CONST = 1, HL_POST_RCP_ROW = 2, HL_POST_MEAN = 3 };
+int hl_segment_reduce(const int32_t* rowptr, const int32_t* colidx, int32_t nrows,
+                      const float* src, int64_t ld_src, const float* src_scale,
+                      float* dst, int64_t ld_dst, int32_t width,
+                      int post, const float* row_scale, float cscale, hl_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Two-endpoint gather per edge (no atomics):
+ *   dst[e,:] = cscale * ( f(src[tail[e],:]) + f(src[head[e],:]) ),  f(v_n) = node_rcp ? (1/node_rcp[n]) * v_n : v_n
+ * Replaces: torch.sparse.mm(par.abs().transpose(0,1), x_t)/2  lib/Hodge_Cheb_Conv.py:295 (=:101),
+ *           lib/Hodge_ST_Model.py:848; and the adjoint of :294.
+ * -------------------------------------------------------------------------------------------- */
+int hl_endpoint_gather(const int32_t* tail, const int32_t* head, int32_t nedges,
+                       const float* src, int64_t ld_src, const float* node_rcp,
+                       float* dst, int64_t ld_dst, int32_t width, float cscale, hl_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Owner gather (adjoint of hl_segment_reduce w.r.t. src, fused with the gate's adjoint):
+ *   dsrc[m,:]  = owner[m] < 0 ? 0 : g[owner[m],:] * w_m * (src_scale ? src_scale[m] : 1)
+ *   dscale[m]  = owner[m] < 0 ? 0 : w_m * <g[owner[m],:], src[m,:]>        (if dscale != NULL)
+ *   w_m        = owner_scale ? owner_scale[owner[m]] : 1                   (1/max(count,1))
+ * Replaces: autograd of scatter_mean / global_mean_pool / `x * att` (lib/Hodge_ST_Model.py:141-150).
+ * -------------------------------------------------------------------------------------------- */
+int hl_owner_gather(const int32_t* owner, int32_t nsrc, const float* g, int64_t ld_g,
+                    const float* owner_scale, const float* src_scale,
+                    const float* src, int64_t ld_src,
+                    float* dsrc, int64_t ld_dsrc, float* dscale, int32_t width, hl_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Attention gate (lib/Hodge_Cheb_Conv.py:299-304):
+ *   pre[r] = ((1-lambda) <qc[r,:], k[r,:]> + lambda <qs[r,:], k[r,:]>) / sqrt(dk)
+ *   a[r]   = sigma(pre[r]),  sigma = HL_SIGMA_SIGMOID | HL_SIGMA_RELU
+ * bwd: given da[r] -> dqc, dqs, dk rows.
+ * -------------------------------------------------------------------------------------------- */
+enum { HL_SIGMA_SIGMOID = 0, HL_SIGMA_RELU = 1 };
+int hl_att_gate_fwd(const float* qc, const float* qs, const float* k, int32_t nrows, int32_t dk,
+                    float lambda, int sigma, float* a, hl_stream_t stream);
+int hl_att_gate_bwd(const float* qc, const float* qs, const float* k, const float* a, const float* da,
+                    int32_t nrows, int32_t dk, float lambda, int sigma,
+                    float* dqc, float* dqs, float* dkk, hl_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Training-mode BatchNorm over rows + activation, writing into a column slice of a wider buffer
+ * (kills the torch.cat of the dense connections).  Two deterministic stages: per-block column
+ * partial sums (Welford-free: sum and sum of squares in fp32 with fp64 finalisation), then apply.
+ * Replaces: gnn.BatchNorm / nn.BatchNorm1d + ReLU/LeakyReLU, lib/Hodge_ST_Model.py:580-586,
+ * lib/Hodge_Cheb_Conv.py:278-282, and torch.cat lib/Hodge_ST_Model.py:632-633.
+ *   y = act( (x - mean) * rsqrt(var_biased + eps) * gamma + beta ),  act: slope 0 = ReLU, 1 = identity
+ * stats[0:F] = mean, stats[F:2F] = biased var (both fp32).  running stats are the caller's.
+ * -------------------------------------------------------------------------------------------- */
+size_t hl_bn_workspace(int32_t nrows, int32_t width);
+int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_t width,
+                  const float* gamma, const float* beta, float eps, float slope,
+                  float* y, int64_t ld_y, float* stats, void* workspace, size_t workspace_bytes,
+                  hl_stream_t stream);
+int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64_t ld_y,
+                  const float* dy, int64_t ld_dy, int32_t nrows, int32_t width,
+                  const float* gamma, const float* stats, float eps, float slope,
+                  float* dx, int64_t ld_dx, float* dgamma, float* dbeta,
+                  void* workspace, size_t workspace_bytes, hl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HLHGAT_H_ */

@@ -1,0 +1,63 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/hlhgat.h declares, and the product path refuses CPU tensors instead of falling back."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import hlhgat_b200 as H
+from hlhgat_b200 import _native as N
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "hlhgat.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hl_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_built_and_exports_every_declared_symbol():
+    H.build()
+    handle = ctypes.CDLL(H.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 17
+    for name in names:
+        assert hasattr(handle, name), f"{name} declared in include/hlhgat.h but not exported"
+    assert sorted(N.exported_symbols()) == names, "ctypes binding and header drifted apart"
+    assert N.lib().hl_version() == 1
+    assert N.lib().hl_status_string(0) == b"ok"
+
+
+def test_no_cpu_fallback():
+    conv = H.HodgeLaguerreConv(4, 5, 3)
+    ei = torch.tensor([[0, 1], [1, 0]])
+    with pytest.raises(H.HlError):
+        conv(torch.randn(2, 4), ei, torch.ones(2))
+    with pytest.raises(H.HlError):
+        H.functional.bn_act_train(torch.randn(4, 4), torch.ones(4), torch.zeros(4))
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(N, "_lib", None)
+    monkeypatch.setattr(N, "LIB_PATH", "/nonexistent/libhlhgat.so")
+    with pytest.raises(H.HlError, match="no CPU or PyTorch fallback"):
+        N.lib()
+
+
+def test_state_dict_contract_matches_reference_names():
+    """Key names / shapes of SURVEY.md section 4 (checkpoint contract)."""
+    from hlhgat_b200.lib.Hodge_ST_Model import HL_HGCNN_zinc_dense_int3_pyr
+    from conftest import load_golden
+    z = load_golden("zinc_model.pt")
+    m = HL_HGCNN_zinc_dense_int3_pyr(K=2, **z["ctor"])
+    m.load_state_dict(z["runs"][2]["state"], strict=True)
+    keys = set(m.state_dict())
+    assert "HL_init_conv.module_0.lins.1.weight" in keys and "HL_init_conv.module_1.module.running_var" in keys
+    assert "NEInt00.WV_Node.0.weight" in keys and "NEConv10.module_4.bias" in keys and "out.weight" in keys
+    conv = H.HodgeLaguerreConv(3, 7, 4)
+    assert [tuple(l.weight.shape) for l in conv.lins] == [(7, 3)] * 4 and conv.bias.abs().sum() == 0
+    with pytest.raises(AssertionError):
+        H.HodgeLaguerreConv(3, 7, 0)

@@ -1,0 +1,322 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden vectors
+recorded from the unmodified reference modules.  Floating point bar (BASELINE.json north_star):
+rtol 1e-4 on outputs and gradients; the SpMM / transfer kernels are additionally bit-exact."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+import hlhgat_b200 as H
+from hlhgat_b200 import functional as F_hl
+from hlhgat_b200 import _native as N
+from hlhgat_b200.simplex import CsrOperator, Incidence, csr_from_coo
+from hlhgat_b200.synthetic import make_batch, batch_to
+from oracle import hodge_oracle as O
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+DEV = "cuda:0"
+
+
+def close(a, b, rtol=RTOL, atol=1e-5):
+    a, b = a.detach().cpu(), b.detach().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert torch.allclose(a, b, rtol=rtol, atol=atol), f"max abs err {(a - b).abs().max().item():.3e}"
+
+
+# ------------------------------------------------------------------------------------------
+def test_csr_from_coo_matches_stable_sort():
+    g = torch.Generator().manual_seed(0)
+    nrows, nnz = 37, 500
+    row = torch.randint(0, nrows, (nnz,), generator=g)
+    col = torch.randint(0, 50, (nnz,), generator=g)
+    val = torch.randn(nnz, generator=g)
+    rp, ci, vv, perm = csr_from_coo(row.to(DEV), col.to(DEV), val.to(DEV), nrows, want_perm=True)
+    order = torch.sort(row, stable=True)[1]
+    assert torch.equal(perm.cpu().long(), order)
+    assert torch.equal(ci.cpu().long(), col[order]) and torch.equal(vv.cpu(), val[order])
+    counts = torch.bincount(row, minlength=nrows)
+    assert torch.equal(rp.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)]))
+    # tie-break by column, rows out of range dropped, float ids with +inf dropped
+    rp2, ci2, _, _ = csr_from_coo(row.to(DEV), col.to(DEV), None, nrows, tie=N.HL_TIE_COLUMN)
+    key = row * 1000 + col
+    assert torch.equal(ci2.cpu().long(), col[torch.sort(key, stable=True)[1]])
+    rf = row.float()
+    rf[::7] = float("inf")
+    rp3, ci3, _, _ = csr_from_coo(rf.to(DEV), None, None, nrows, row_is_float=True)
+    keep = torch.isfinite(rf)
+    kept_order = torch.arange(nnz)[keep][torch.sort(row[keep], stable=True)[1]]
+    assert int(rp3[-1]) == int(keep.sum())
+    assert torch.equal(ci3.cpu().long()[: int(rp3[-1])], kept_order)
+    # empty input
+    rp4, _, _, _ = csr_from_coo(torch.zeros(0, dtype=torch.long, device=DEV), None, None, 5)
+    assert rp4.cpu().tolist() == [0] * 6
+
+
+@pytest.mark.parametrize("idx", range(21))
+def test_conv_vs_golden_reference(idx):
+    c = load_golden("conv.pt")["cases"][idx]
+    cls = H.HodgeLaguerreConv if c["family"] == "laguerre" else H.HodgeChebConv
+    conv = cls(c["fin"], c["fout"], c["K"]).to(DEV)
+    conv.load_state_dict(c["state"], strict=True)
+    x = c["x"].to(DEV).requires_grad_(True)
+    y = conv(x, c["edge_index"].to(DEV), c["edge_weight"].to(DEV))
+    close(y, c["y"])
+    g = torch.autograd.grad((y * c["wsum"].to(DEV)).sum(), [x] + list(conv.parameters()))
+    close(g[0], c["gx"])
+    for (n, _), t in zip(conv.named_parameters(), g[1:]):
+        close(t, c["gp"][n])
+
+
+@pytest.mark.parametrize("family", ["laguerre", "cheb"])
+@pytest.mark.parametrize("width", [64, 128, 256, 28, 10, 7, 300])
+def test_poly_basis_bit_exact_vs_oracle(family, width):
+    """T_k computed by the SpMM kernels equals the CPU reference recurrence BIT FOR BIT."""
+    b = make_batch("zinc", 24, seed=3)
+    K = 5
+    for ei, ew, r in ((b.edge_index_t, b.edge_weight_t, b.x_t.shape[0]), (b.edge_index_s, b.edge_weight_s, b.x_s.shape[0])):
+        x = torch.randn(r, width)
+        op = CsrOperator(ei.to(DEV), ew.to(DEV), r)
+        (t,) = F_hl.poly_basis_fwd(F_hl._FAMILY[family], K, [op], [x.to(DEV)], width)
+        t0, t1 = x, None
+        for k in range(K - 1):
+            if family == "laguerre":
+                if k == 0:
+                    t1 = x - O.propagate(x, ei, ew)
+                else:
+                    t2 = (-O.propagate(t1, ei, ew) + (2 * k + 1) * t1 - k * t0) / (k + 1)
+                    t0, t1 = t1, t2
+            else:
+                if k == 0:
+                    t1 = O.propagate(x, ei, ew)
+                else:
+                    t2 = 2. * O.propagate(t1, ei, ew) - t0
+                    t0, t1 = t1, t2
+            assert torch.equal(t[k].cpu(), t1), f"order {k + 1}: max err {(t[k].cpu() - t1).abs().max()}"
+
+
+def test_fused_two_operator_launch_equals_separate():
+    b = make_batch("zinc", 16, seed=5)
+    n, e = b.x_t.shape[0], b.x_s.shape[0]
+    op_t = CsrOperator(b.edge_index_t.to(DEV), b.edge_weight_t.to(DEV), n)
+    op_s = CsrOperator(b.edge_index_s.to(DEV), b.edge_weight_s.to(DEV), e)
+    xt, xs = torch.randn(n, 64, device=DEV), torch.randn(e, 64, device=DEV)
+    both = F_hl.poly_basis_fwd(N.HL_LAGUERRE, 4, [op_t, op_s], [xt, xs], 64)
+    (a,) = F_hl.poly_basis_fwd(N.HL_LAGUERRE, 4, [op_t], [xt], 64)
+    (c,) = F_hl.poly_basis_fwd(N.HL_LAGUERRE, 4, [op_s], [xs], 64)
+    assert torch.equal(both[0], a) and torch.equal(both[1], c)
+
+
+def test_conv_3d_input_and_fastconv():
+    for c in load_golden("fastconv.pt"):
+        conv = H.HodgeLaguerreFastConv(5, 6, c["K"]).to(DEV)
+        conv.load_state_dict(c["state"])
+        close(conv(c["x"].to(DEV), (c["edge_index"].to(DEV), c["edge_weight"].to(DEV))), c["y"])
+        # gradients of the quirk path against the oracle's autograd
+        oc = O.HodgeLaguerreFastConv(5, 6, c["K"])
+        oc.load_state_dict(c["state"])
+        xo = c["x"].clone().requires_grad_(True)
+        go = torch.autograd.grad(oc(xo, c["edge_index"], c["edge_weight"]).pow(2).sum(), [xo] + list(oc.parameters()))
+        xg = c["x"].to(DEV).requires_grad_(True)
+        gg = torch.autograd.grad(conv(xg, (c["edge_index"].to(DEV), c["edge_weight"].to(DEV))).pow(2).sum(),
+                                 [xg] + list(conv.parameters()))
+        for a, b in zip(gg, go):
+            close(a, b)
+
+
+def test_transfer_bit_exact_and_grads():
+    gold = load_golden("neint.pt")
+    tiny = gold["tiny"]
+    ei = tiny["edge_index"].to(DEV)
+    inc = Incidence(ei, 4)
+    s2t = F_hl.edge_to_node(torch.tensor([[1.], [2.], [3.], [4.]], device=DEV), tiny["D"].to(DEV), inc)
+    t2s = F_hl.node_to_edge(torch.tensor([[0.], [10.], [20.], [30.]], device=DEV), inc)
+    assert torch.equal(s2t.cpu(), tiny["x_s2t"]) and torch.equal(t2s.cpu(), tiny["x_t2s"])
+    b = make_batch("zinc", 32, seed=1)
+    n, e = b.x_t.shape[0], b.x_s.shape[0]
+    for width in (64, 192, 704, 6):
+        x_t = torch.randn(n, width, requires_grad=True)
+        x_s = torch.randn(e, width, requires_grad=True)
+        D = O.degree(b.edge_index.view(-1), n) + 1e-6
+        o_s2t, o_t2s = O.transfer(x_t, x_s, O.adj2par1(b.edge_index, n, e), D)
+        inc = Incidence(b.edge_index.to(DEV), n)
+        xt_g, xs_g = x_t.detach().to(DEV).requires_grad_(True), x_s.detach().to(DEV).requires_grad_(True)
+        g_s2t = F_hl.edge_to_node(xs_g, D.to(DEV), inc)
+        g_t2s = F_hl.node_to_edge(xt_g, inc)
+        assert torch.equal(g_s2t.cpu(), o_s2t.detach()) and torch.equal(g_t2s.cpu(), o_t2s.detach())
+        w1, w2 = torch.randn(n, width), torch.randn(e, width)
+        go = torch.autograd.grad((o_s2t * w1).sum() + (o_t2s * w2).sum(), [x_t, x_s])
+        gg = torch.autograd.grad((g_s2t * w1.to(DEV)).sum() + (g_t2s * w2.to(DEV)).sum(), [xt_g, xs_g])
+        close(gg[0], go[0])
+        close(gg[1], go[1])
+
+
+@pytest.mark.parametrize("idx", range(3))
+def test_node_edge_int_vs_golden_reference(idx):
+    c = load_golden("neint.pt")["cases"][idx]
+    n, e = c["x_t"].shape[0], c["x_s"].shape[0]
+    sig = torch.nn.Sigmoid() if c["sigma"] == "sigmoid" else torch.nn.ReLU()
+    mod = H.NodeEdgeInt(d=c["d"], dk=c["dk"], dv=c["dv"], only_att=c["only_att"], sigma=sig, l=c["l"]).to(DEV)
+    mod.load_state_dict(c["state"], strict=False)
+    mod.train()
+    par = H.adj2par1(c["edge_index"].to(DEV), n, e)
+    x_t, x_s = c["x_t"].to(DEV).requires_grad_(True), c["x_s"].to(DEV).requires_grad_(True)
+    y_t, y_s = mod(x_t, x_s, par, c["D"].to(DEV))
+    close(y_t, c["y_t"])
+    close(y_s, c["y_s"])
+    loss = (y_t * c["w_t"].to(DEV)).sum() + (y_s * c["w_s"].to(DEV)).sum()
+    g = torch.autograd.grad(loss, [x_t, x_s] + list(mod.parameters()))
+    close(g[0], c["gx_t"], atol=2e-5)
+    close(g[1], c["gx_s"], atol=2e-5)
+    for (nm, _), t in zip(mod.named_parameters(), g[2:]):
+        close(t, c["gp"][nm], atol=2e-5)
+
+
+def test_foreign_sparse_par_is_accepted():
+    """NodeEdgeInt must also take a `par` built by the reference's own adj2par1 (plain sparse COO)."""
+    c = load_golden("neint.pt")["cases"][0]
+    n, e = c["x_t"].shape[0], c["x_s"].shape[0]
+    par = O.adj2par1(c["edge_index"], n, e).to(DEV)
+    mod = H.NodeEdgeInt(d=c["d"], dk=c["dk"], dv=c["dv"]).to(DEV)
+    mod.load_state_dict(c["state"], strict=False)
+    y_t, y_s = mod(c["x_t"].to(DEV), c["x_s"].to(DEV), par, c["D"].to(DEV))
+    close(y_t, c["y_t"])
+    close(y_s, c["y_s"])
+
+
+def test_pool_block_vs_golden_reference():
+    p = load_golden("pool.pt")
+    n, e = p["x_t"].shape[0], p["x_s"].shape[0]
+    pool = H.SAPool(d=6, dk=4).to(DEV)
+    pool.load_state_dict(p["state"], strict=True)
+    par = H.adj2par1(p["fine"]["edge_index"].to(DEV), n, e)
+    coarse = SimpleNamespace(**{k: v for k, v in p["coarse"].items() if torch.is_tensor(v)})
+    fine = SimpleNamespace()
+    res = pool(p["x_t"].to(DEV), p["x_s"].to(DEV), par, p["D"].to(DEV), [fine, coarse],
+               [p["c_node"].float().to(DEV)], [p["c_edge"].to(DEV)], 0, device=DEV)
+    close(res[0], p["x_t1"])
+    close(res[1], p["x_s1"])
+    close(res[3], p["D1"])
+    close(res[9], p["att_t"])
+    close(res[10], p["att_s"])
+    assert torch.equal(res[2].to_dense().cpu(), p["par1_dense"])
+
+
+def test_segment_mean_and_gate_grads_vs_oracle():
+    torch.manual_seed(0)
+    r, f, ncl = 300, 48, 40
+    src = torch.randn(r, f, requires_grad=True)
+    att = torch.rand(r, 1, requires_grad=True)
+    pos = torch.randint(0, ncl, (r, 1)).float()
+    pos[::9] = float("inf")
+    keep = ~torch.isinf(pos).view(-1)
+    ref = O.scatter_mean((src * att)[keep], pos[keep].long())
+    w = torch.randn_like(ref)
+    go = torch.autograd.grad((ref * w).sum(), [src, att])
+    sg, ag = src.detach().to(DEV).requires_grad_(True), att.detach().to(DEV).requires_grad_(True)
+    out = F_hl.segment_mean(sg, F_hl.Segments.from_index(pos.to(DEV)), ag)
+    assert torch.equal(out.cpu(), ref.detach())
+    gg = torch.autograd.grad((out * w.to(DEV)).sum(), [sg, ag])
+    close(gg[0], go[0])
+    close(gg[1], go[1])
+    # readout: contiguous segments
+    counts = torch.tensor([5, 0, 17, 278])
+    bvec = torch.repeat_interleave(torch.arange(4), counts)
+    close(F_hl.segment_mean(sg, F_hl.Segments.from_counts(counts.to(DEV))), O.global_mean_pool(src, bvec, 4))
+    # gate
+    for sigma in ("sigmoid", "relu"):
+        qc, qs, k = (torch.randn(r, 32, requires_grad=True) for _ in range(3))
+        act = torch.sigmoid if sigma == "sigmoid" else torch.relu
+        a_ref = act((0.3 * (qc * k).sum(1, keepdim=True) + 0.7 * (qs * k).sum(1, keepdim=True)) / 32 ** 0.5)
+        wa = torch.randn(r, 1)
+        go = torch.autograd.grad((a_ref * wa).sum(), [qc, qs, k])
+        dq = [t.detach().to(DEV).requires_grad_(True) for t in (qc, qs, k)]
+        a = F_hl.att_gate(dq[0], dq[1], dq[2], 0.7, sigma)
+        close(a, a_ref)
+        for x, y in zip(torch.autograd.grad((a * wa.to(DEV)).sum(), dq), go):
+            close(x, y)
+
+
+@pytest.mark.parametrize("shape", [(1000, 64), (3001, 256), (257, 10), (5, 7)])
+@pytest.mark.parametrize("slope", [0.0, 0.1, 1.0])
+def test_bn_act_vs_torch(shape, slope):
+    torch.manual_seed(1)
+    x = (torch.randn(*shape) * 3 + 5).requires_grad_(True)
+    gamma, beta = torch.rand(shape[1], requires_grad=True), torch.randn(shape[1], requires_grad=True)
+    z = torch.nn.functional.batch_norm(x, None, None, gamma, beta, True, 0.1, 1e-5)
+    ref = torch.nn.functional.leaky_relu(z, slope) if slope != 1.0 else z
+    w = torch.randn_like(ref)
+    go = torch.autograd.grad((ref * w).sum(), [x, gamma, beta])
+    xs = [t.detach().to(DEV).requires_grad_(True) for t in (x, gamma, beta)]
+    y, stats = F_hl.bn_act_train(xs[0], xs[1], xs[2], 1e-5, slope)
+    close(y, ref)
+    close(stats[: shape[1]], x.mean(0))
+    close(stats[shape[1]:], x.var(0, unbiased=False))
+    for a, b in zip(torch.autograd.grad((y * w.to(DEV)).sum(), xs), go):
+        close(a, b, atol=1e-4)
+
+
+@pytest.mark.parametrize("K", [2, 3])
+def test_zinc_model_vs_golden_reference(K):
+    from hlhgat_b200.lib.Hodge_ST_Model import HL_HGCNN_zinc_dense_int3_pyr
+    z = load_golden("zinc_model.pt")
+    run = z["runs"][K]
+    model = HL_HGCNN_zinc_dense_int3_pyr(K=K, **z["ctor"]).to(DEV)
+    model.load_state_dict(run["state"], strict=True)
+    model.train()
+    data = SimpleNamespace(**{k: v.to(DEV) for k, v in z["batch"].items()})
+    pred = model(data, device=DEV)
+    close(pred, run["pred"], atol=2e-5)
+    loss = torch.nn.functional.l1_loss(pred, data.y.view(-1, 1))
+    g = torch.autograd.grad(loss, list(model.parameters()), allow_unused=True)
+    for (n, _), t in zip(model.named_parameters(), g):
+        ref = run["grads"][n]
+        assert (t is None) == (ref is None), n
+        if t is not None:
+            close(t, ref, rtol=1e-3, atol=2e-5)      # 6-graph batch: BN over ~60 rows amplifies fp32 noise
+
+
+def test_zinc_model_full_size_vs_oracle():
+    """BASELINE config-1 model (filters 64/128/256, K=2) on a 64-graph ZINC-shaped batch: forward
+    and all parameter gradients against the CPU oracle."""
+    from hlhgat_b200.lib.Hodge_ST_Model import HL_HGCNN_zinc_dense_int3_pyr
+    torch.manual_seed(0)
+    ctor = dict(channels=[2, 2, 2], filters=[64, 128, 256], mlp_channels=[], K=2, node_dim=21, edge_dim=3, keig=7)
+    ref = O.HL_HGCNN_zinc_dense_int3_pyr(**ctor)
+    ref.train()
+    b = make_batch("zinc", 64, seed=11)
+    pred_ref = ref(b)
+    loss_ref = torch.nn.functional.l1_loss(pred_ref, b.y)
+    g_ref = torch.autograd.grad(loss_ref, list(ref.parameters()), allow_unused=True)
+    model = HL_HGCNN_zinc_dense_int3_pyr(**ctor).to(DEV)
+    model.load_state_dict(ref.state_dict(), strict=True)
+    model.train()
+    d = batch_to(b, DEV)
+    pred = model(d, device=DEV)
+    close(pred, pred_ref, rtol=1e-4, atol=1e-4)
+    loss = torch.nn.functional.l1_loss(pred, d.y)
+    g = torch.autograd.grad(loss, list(model.parameters()), allow_unused=True)
+    worst = 0.0
+    for (n, _), a, r in zip(model.named_parameters(), g, g_ref):
+        if r is None:
+            assert a is None, n
+            continue
+        err = (a.cpu() - r).norm() / (r.norm() + 1e-12)
+        worst = max(worst, float(err))
+        assert err < 1e-3, (n, float(err))
+    print("worst relative grad error", worst)
+
+
+def test_determinism_two_runs_bit_identical():
+    from hlhgat_b200.lib.Hodge_ST_Model import HL_HGCNN_zinc_dense_int3_pyr
+    torch.manual_seed(0)
+    model = HL_HGCNN_zinc_dense_int3_pyr(channels=[1, 1], filters=[32, 64], K=3, node_dim=21, edge_dim=3, keig=7).to(DEV)
+    d = batch_to(make_batch("zinc", 32, seed=2), DEV)
+    outs = []
+    for _ in range(2):
+        model.zero_grad()
+        p = model(d, device=DEV)
+        p.abs().mean().backward()
+        outs.append((p.detach().clone(), model.NEConv00.module_0.lins[1].weight.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
