@@ -38,6 +38,7 @@ _SIGNATURES = {
     "hl_status_string": (C.c_char_p, [C.c_int]),
     "hl_last_cuda_error": (C.c_char_p, []),
     "hl_device_sm_count": (C.c_int, []),
+    "hl_launch_count": (C.c_ulonglong, []),
     "hl_csr_from_coo_workspace": (_sz, [_i64, _i64]),
     "hl_csr_from_coo": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, C.c_int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hl_poly_spmm": (C.c_int, [C.POINTER(SpmmProblem), C.c_int, _i32, C.c_int, C.POINTER(_f32), _vp]),
@@ -49,9 +50,9 @@ _SIGNATURES = {
     "hl_att_gate_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _f32, C.c_int, _vp, _vp]),
     "hl_att_gate_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, C.c_int, _vp, _vp, _vp, _vp]),
     "hl_bn_workspace": (_sz, [_i32, _i32]),
-    "hl_bn_act_fwd": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "hl_bn_act_fwd": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "hl_bn_act_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32,
-                                _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+                                _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

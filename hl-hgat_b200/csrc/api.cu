@@ -1,4 +1,5 @@
 // Library-level entry points: version, status strings, last CUDA error.
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 
@@ -7,6 +8,9 @@
 namespace hl {
 
 thread_local char g_last_error[256] = "";
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int record_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_last_error, sizeof(g_last_error), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
@@ -14,6 +18,9 @@ int record_cuda_error(cudaError_t e, const char* where) {
 }
 
 }  // namespace hl
+
+namespace hl { unsigned long long launches(); }
+extern "C" unsigned long long hl_launch_count(void) { return hl::launches(); }
 
 extern "C" int hl_version(void) { return HL_ABI_VERSION; }
 

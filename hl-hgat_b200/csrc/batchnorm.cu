@@ -15,8 +15,9 @@ static inline int bn_row_blocks(int32_t nrows) { return (nrows + kBnRowsPerBlock
 // partial[(blk * 2 + {0,1}) * width + col] = {mean_b, M2_b} of the block's rows (fp64)
 template <int V>
 __global__ void __launch_bounds__(kBnThreads)
-bn_stats_partial_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows, int32_t width,
-                        double* __restrict__ partial) {
+bn_stats_partial_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows_cap, const int32_t* __restrict__ nvalid,
+                        int32_t width, double* __restrict__ partial) {
+  const int32_t nrows = nvalid ? min(__ldg(nvalid), nrows_cap) : nrows_cap;
   __shared__ float sh[2][kBnWarps][32 * V];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.y * (32 * V) + lane * V;
@@ -26,7 +27,7 @@ bn_stats_partial_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows
   Pack<V> shift, s1, s2;
 #pragma unroll
   for (int i = 0; i < V; ++i) shift.v[i] = s1.v[i] = s2.v[i] = 0.f;
-  if (act) {
+  if (act && r0 < r1) {
     shift = ld_pack<V>(x + (int64_t)r0 * ld_x + col);
     for (int r = r0 + warp; r < r1; r += kBnWarps) {
       Pack<V> v = ld_pack<V>(x + (int64_t)r * ld_x + col);
@@ -45,7 +46,7 @@ bn_stats_partial_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows
   }
   __syncthreads();
   if (warp == 0 && act) {
-    const double n = (double)(r1 - r0);
+    const double n = (double)max(r1 - r0, 1);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       double a = 0.0, b = 0.0;
@@ -60,13 +61,15 @@ bn_stats_partial_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows
   }
 }
 
-__global__ void bn_stats_final_kernel(const double* __restrict__ partial, int nblk, int32_t nrows, int32_t width,
-                                      float* __restrict__ stats) {
+__global__ void bn_stats_final_kernel(const double* __restrict__ partial, int nblk, int32_t nrows_cap,
+                                      const int32_t* __restrict__ nvalid, int32_t width, float* __restrict__ stats) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= width) return;
+  const int32_t nrows = nvalid ? min(__ldg(nvalid), nrows_cap) : nrows_cap;
   double n = 0.0, mean = 0.0, m2 = 0.0;
   for (int b = 0; b < nblk; ++b) {                            // Chan et al. pairwise merge, fixed order
     const double nb = (double)(min((b + 1) * kBnRowsPerBlock, nrows) - b * kBnRowsPerBlock);
+    if (nb <= 0.0) break;
     const double mb = partial[((int64_t)b * 2 + 0) * width + c];
     const double qb = partial[((int64_t)b * 2 + 1) * width + c];
     const double tot = n + nb;
@@ -76,30 +79,36 @@ __global__ void bn_stats_final_kernel(const double* __restrict__ partial, int nb
     n = tot;
   }
   stats[c] = (float)mean;
-  stats[width + c] = (float)(m2 / n);
+  stats[width + c] = n > 0.0 ? (float)(m2 / n) : 0.f;
 }
 
 template <int V>
 __global__ void __launch_bounds__(256)
-bn_apply_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows, int32_t width,
+bn_apply_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows, const int32_t* __restrict__ nvalid, int32_t width,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
                 float eps, float slope, float* __restrict__ y, int64_t ld_y) {
   const int chunks = width / V;
   const int64_t total = (int64_t)nrows * chunks;
+  const int32_t nv = nvalid ? min(__ldg(nvalid), nrows) : nrows;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(idx / chunks);
     const int col = (int)(idx - (int64_t)r * chunks) * V;
-    Pack<V> v = ld_pack<V>(x + (int64_t)r * ld_x + col);
     Pack<V> o;
+    if (r < nv) {
+      Pack<V> v = ld_pack<V>(x + (int64_t)r * ld_x + col);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float mean = __ldg(stats + col + i);
-      const float rstd = rsqrtf(__ldg(stats + width + col + i) + eps);
-      const float g = gamma ? __ldg(gamma + col + i) : 1.f;
-      const float b = beta ? __ldg(beta + col + i) : 0.f;
-      float t = (v.v[i] - mean) * rstd * g + b;
-      o.v[i] = t > 0.f ? t : t * slope;
+      for (int i = 0; i < V; ++i) {
+        const float mean = __ldg(stats + col + i);
+        const float rstd = rsqrtf(__ldg(stats + width + col + i) + eps);
+        const float g = gamma ? __ldg(gamma + col + i) : 1.f;
+        const float b = beta ? __ldg(beta + col + i) : 0.f;
+        float t = (v.v[i] - mean) * rstd * g + b;
+        o.v[i] = t > 0.f ? t : t * slope;
+      }
+    } else {                                                 // ghost (padding) rows stay exactly zero
+#pragma unroll
+      for (int i = 0; i < V; ++i) o.v[i] = 0.f;
     }
     st_pack<V>(y + (int64_t)r * ld_y + col, o);
   }
@@ -109,9 +118,10 @@ bn_apply_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows, int32_
 template <int V>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_partial_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ y, int64_t ld_y,
-                      const float* __restrict__ dy, int64_t ld_dy, int32_t nrows, int32_t width,
-                      const float* __restrict__ stats, float eps, float slope, double* __restrict__ partial) {
+                      const float* __restrict__ dy, int64_t ld_dy, int32_t nrows_cap, const int32_t* __restrict__ nvalid,
+                      int32_t width, const float* __restrict__ stats, float eps, float slope, double* __restrict__ partial) {
   __shared__ float sh[2][kBnWarps][32 * V];
+  const int32_t nrows = nvalid ? min(__ldg(nvalid), nrows_cap) : nrows_cap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.y * (32 * V) + lane * V;
   const int r0 = blockIdx.x * kBnRowsPerBlock;
@@ -179,28 +189,34 @@ __global__ void bn_bwd_final_kernel(const double* __restrict__ partial, int nblk
 template <int V>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ y, int64_t ld_y,
-                    const float* __restrict__ dy, int64_t ld_dy, int32_t nrows, int32_t width,
+                    const float* __restrict__ dy, int64_t ld_dy, int32_t nrows, const int32_t* __restrict__ nvalid, int32_t width,
                     const float* __restrict__ gamma, const float* __restrict__ stats, const float* __restrict__ sums,
                     float eps, float slope, float* __restrict__ dx, int64_t ld_dx) {
   const int chunks = width / V;
   const int64_t total = (int64_t)nrows * chunks;
-  const float inv_n = 1.f / (float)nrows;
+  const int32_t nv = nvalid ? min(__ldg(nvalid), nrows) : nrows;
+  const float inv_n = 1.f / (float)max(nv, 1);
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(idx / chunks);
     const int col = (int)(idx - (int64_t)r * chunks) * V;
-    Pack<V> xv = ld_pack<V>(x + (int64_t)r * ld_x + col);
-    Pack<V> yv = ld_pack<V>(y + (int64_t)r * ld_y + col);
-    Pack<V> gv = ld_pack<V>(dy + (int64_t)r * ld_dy + col);
     Pack<V> o;
+    if (r < nv) {
+      Pack<V> xv = ld_pack<V>(x + (int64_t)r * ld_x + col);
+      Pack<V> yv = ld_pack<V>(y + (int64_t)r * ld_y + col);
+      Pack<V> gv = ld_pack<V>(dy + (int64_t)r * ld_dy + col);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float mean = __ldg(stats + col + i);
-      const float rstd = rsqrtf(__ldg(stats + width + col + i) + eps);
-      const float g = gamma ? __ldg(gamma + col + i) : 1.f;
-      const float dz = yv.v[i] > 0.f ? gv.v[i] : gv.v[i] * slope;
-      const float xh = (xv.v[i] - mean) * rstd;
-      o.v[i] = g * rstd * (dz - __ldg(sums + col + i) * inv_n - xh * __ldg(sums + width + col + i) * inv_n);
+      for (int i = 0; i < V; ++i) {
+        const float mean = __ldg(stats + col + i);
+        const float rstd = rsqrtf(__ldg(stats + width + col + i) + eps);
+        const float g = gamma ? __ldg(gamma + col + i) : 1.f;
+        const float dz = yv.v[i] > 0.f ? gv.v[i] : gv.v[i] * slope;
+        const float xh = (xv.v[i] - mean) * rstd;
+        o.v[i] = g * rstd * (dz - __ldg(sums + col + i) * inv_n - xh * __ldg(sums + width + col + i) * inv_n);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) o.v[i] = 0.f;
     }
     st_pack<V>(dx + (int64_t)r * ld_dx + col, o);
   }
@@ -222,8 +238,8 @@ extern "C" size_t hl_bn_workspace(int32_t nrows, int32_t width) {
 
 extern "C" int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_t width,
                              const float* gamma, const float* beta, float eps, float slope,
-                             float* y, int64_t ld_y, float* stats, void* workspace, size_t workspace_bytes,
-                             hl_stream_t stream) {
+                             float* y, int64_t ld_y, float* stats, const int32_t* nvalid,
+                             void* workspace, size_t workspace_bytes, hl_stream_t stream) {
   using namespace hl;
   if (nrows < 1 || width < 1 || !x || !y || !stats) return HL_ERR_INVALID;
   if (!workspace || workspace_bytes < hl_bn_workspace(nrows, width)) return HL_ERR_WORKSPACE;
@@ -233,16 +249,16 @@ extern "C" int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_
   V = min(V, vec_for(y, ld_y, width, V));
   const int nblk = bn_row_blocks(nrows);
   dim3 grid(nblk, (width + 32 * V - 1) / (32 * V));
-  if (V == 4) bn_stats_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, width, partial);
-  else if (V == 2) bn_stats_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, width, partial);
-  else bn_stats_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, width, partial);
+  if (V == 4) bn_stats_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
+  else if (V == 2) bn_stats_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
+  else bn_stats_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
   HL_LAUNCH_CHECK("bn_stats_partial_kernel");
-  bn_stats_final_kernel<<<(width + 127) / 128, 128, 0, st>>>(partial, nblk, nrows, width, stats);
+  bn_stats_final_kernel<<<(width + 127) / 128, 128, 0, st>>>(partial, nblk, nrows, nvalid, width, stats);
   HL_LAUNCH_CHECK("bn_stats_final_kernel");
   const int g = ew_grid((int64_t)nrows * (width / V));
-  if (V == 4) bn_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, nrows, width, gamma, beta, stats, eps, slope, y, ld_y);
-  else if (V == 2) bn_apply_kernel<2><<<g, 256, 0, st>>>(x, ld_x, nrows, width, gamma, beta, stats, eps, slope, y, ld_y);
-  else bn_apply_kernel<1><<<g, 256, 0, st>>>(x, ld_x, nrows, width, gamma, beta, stats, eps, slope, y, ld_y);
+  if (V == 4) bn_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else if (V == 2) bn_apply_kernel<2><<<g, 256, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else bn_apply_kernel<1><<<g, 256, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
   HL_LAUNCH_CHECK("bn_apply_kernel");
   return HL_OK;
 }
@@ -250,7 +266,7 @@ extern "C" int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_
 extern "C" int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64_t ld_y,
                              const float* dy, int64_t ld_dy, int32_t nrows, int32_t width,
                              const float* gamma, const float* stats, float eps, float slope,
-                             float* dx, int64_t ld_dx, float* dgamma, float* dbeta,
+                             float* dx, int64_t ld_dx, float* dgamma, float* dbeta, const int32_t* nvalid,
                              void* workspace, size_t workspace_bytes, hl_stream_t stream) {
   using namespace hl;
   if (nrows < 1 || width < 1 || !x || !y || !dy || !dx || !stats) return HL_ERR_INVALID;
@@ -265,16 +281,16 @@ extern "C" int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64
   V = min(V, vec_for(dy, ld_dy, width, V));
   V = min(V, vec_for(dx, ld_dx, width, V));
   dim3 grid(nblk, (width + 32 * V - 1) / (32 * V));
-  if (V == 4) bn_bwd_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, width, stats, eps, slope, partial);
-  else if (V == 2) bn_bwd_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, width, stats, eps, slope, partial);
-  else bn_bwd_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, width, stats, eps, slope, partial);
+  if (V == 4) bn_bwd_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
+  else if (V == 2) bn_bwd_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
+  else bn_bwd_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
   HL_LAUNCH_CHECK("bn_bwd_partial_kernel");
   bn_bwd_final_kernel<<<(width + 127) / 128, 128, 0, st>>>(partial, nblk, width, sums, dgamma, dbeta);
   HL_LAUNCH_CHECK("bn_bwd_final_kernel");
   const int g = ew_grid((int64_t)nrows * (width / V));
-  if (V == 4) bn_bwd_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, width, gamma, stats, sums, eps, slope, dx, ld_dx);
-  else if (V == 2) bn_bwd_apply_kernel<2><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, width, gamma, stats, sums, eps, slope, dx, ld_dx);
-  else bn_bwd_apply_kernel<1><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, width, gamma, stats, sums, eps, slope, dx, ld_dx);
+  if (V == 4) bn_bwd_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx);
+  else if (V == 2) bn_bwd_apply_kernel<2><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx);
+  else bn_bwd_apply_kernel<1><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx);
   HL_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return HL_OK;
 }

@@ -8,6 +8,7 @@ namespace hl {
 
 extern thread_local char g_last_error[256];
 int record_cuda_error(cudaError_t e, const char* where);
+void count_launch();   // bumps the library-wide kernel launch counter (hl_launch_count)
 
 #define HL_CUDA_CHECK(expr)                                         \
   do {                                                              \
@@ -17,6 +18,7 @@ int record_cuda_error(cudaError_t e, const char* where);
 
 #define HL_LAUNCH_CHECK(name)                                      \
   do {                                                             \
+    hl::count_launch();                                            \
     cudaError_t _e = cudaGetLastError();                           \
     if (_e != cudaSuccess) return hl::record_cuda_error(_e, name); \
   } while (0)

@@ -20,9 +20,13 @@ struct SpmmBatch {
 
 constexpr int kThreads = 256;
 
-template <int V, int CH>
+// One group of G lanes per output row; each lane owns CH vectors of V floats (columns
+// col0 + ch*G*V).  The row's (colidx, vals) are read with group-uniform (broadcast) loads, U entries
+// at a time: all U*CH gathers are issued before the ordered multiply/add chain consumes them, which
+// is where the memory-level parallelism comes from on short rows (ZINC: 3-4 nnz per row).
+template <int V, int CH, int U, int EPI>
 __global__ void __launch_bounds__(kThreads)
-poly_spmm_kernel(const SpmmBatch b, const int32_t width, const int32_t G, const int32_t epi,
+poly_spmm_kernel(const SpmmBatch b, const int32_t width, const int32_t G,
                  const float c0, const float c1, const float c2, const float c3) {
   int pb = 0;
   while (pb + 1 < b.n && (int32_t)blockIdx.x >= b.block_start[pb + 1]) ++pb;
@@ -31,9 +35,7 @@ poly_spmm_kernel(const SpmmBatch b, const int32_t width, const int32_t G, const 
   const int rows_per_block = kThreads / G;
   const int gl = threadIdx.x & (G - 1);                       // lane within the row group
   const int row = ((int32_t)blockIdx.x - b.block_start[pb]) * rows_per_block + (int)(threadIdx.x / G);
-  if (row >= P.nrows) return;                                 // uniform per group
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(unsigned)(G - 1)));
+  if (row >= P.nrows) return;
 
   const int col0 = blockIdx.y * (G * V * CH) + gl * V;        // first column of chunk 0
   bool act[CH];
@@ -49,51 +51,34 @@ poly_spmm_kernel(const SpmmBatch b, const int32_t width, const int32_t G, const 
   const int start = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
   const float* __restrict__ xg = P.xg + col0;
   const int64_t ldx = P.ld_xg;
+  const int32_t* __restrict__ colidx = P.colidx;
+  const float* __restrict__ vals = P.vals;
 
-  for (int base = start; base < end; base += G) {
-    const int p = base + gl;
-    int c = 0;
-    float v = 0.f;
-    if (p < end) {
-      c = __ldg(P.colidx + p);
-      v = __ldg(P.vals + p);
+  for (int p = start; p < end; p += U) {
+    int c[U];
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int q = min(p + u, end - 1);                      // clamped: loads stay unconditional
+      c[u] = __ldg(colidx + q);
+      v[u] = __ldg(vals + q);
     }
-    const int cnt = min(G, end - base);
-    int j = 0;
-    for (; j + 4 <= cnt; j += 4) {
-      int cj[4];
-      float vj[4];
+    Pack<V> x[U][CH];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        cj[u] = __shfl_sync(gmask, c, j + u, G);
-        vj[u] = __shfl_sync(gmask, v, j + u, G);
-      }
-      Pack<V> x[4][CH];
+    for (int u = 0; u < U; ++u)
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int ch = 0; ch < CH; ++ch)
+        if (act[ch]) x[u][ch] = ld_pack<V>(xg + (int64_t)c[u] * ldx + ch * G * V);
 #pragma unroll
-        for (int ch = 0; ch < CH; ++ch)
-          if (act[ch]) x[u][ch] = ld_pack<V>(xg + (int64_t)cj[u] * ldx + ch * G * V);
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < U; ++u)
+      if (p + u < end) {
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch)
           if (act[ch])
 #pragma unroll
             for (int i = 0; i < V; ++i)
-              acc[ch].v[i] = __fadd_rn(acc[ch].v[i], __fmul_rn(vj[u], x[u][ch].v[i]));
-    }
-    for (; j < cnt; ++j) {
-      const int cj = __shfl_sync(gmask, c, j, G);
-      const float vj = __shfl_sync(gmask, v, j, G);
-#pragma unroll
-      for (int ch = 0; ch < CH; ++ch)
-        if (act[ch]) {
-          Pack<V> x = ld_pack<V>(xg + (int64_t)cj * ldx + ch * G * V);
-#pragma unroll
-          for (int i = 0; i < V; ++i) acc[ch].v[i] = __fadd_rn(acc[ch].v[i], __fmul_rn(vj, x.v[i]));
-        }
-    }
+              acc[ch].v[i] = __fadd_rn(acc[ch].v[i], __fmul_rn(v[u], x[u][ch].v[i]));
+      }
   }
 
   // ---- fused recurrence epilogue -------------------------------------------------------------
@@ -102,13 +87,13 @@ poly_spmm_kernel(const SpmmBatch b, const int32_t width, const int32_t G, const 
     if (!act[ch]) continue;
     const int col = col0 + ch * G * V;
     Pack<V> o;
-    if (epi == HL_EPI_CHEB_FIRST) {
+    if constexpr (EPI == HL_EPI_CHEB_FIRST) {
       o = acc[ch];
-    } else if (epi == HL_EPI_LAGUERRE_FIRST) {
+    } else if constexpr (EPI == HL_EPI_LAGUERRE_FIRST) {
       Pack<V> a1 = ld_pack_coherent<V>(P.p1 + (int64_t)row * P.ld_p1 + col);
 #pragma unroll
       for (int i = 0; i < V; ++i) o.v[i] = __fsub_rn(a1.v[i], acc[ch].v[i]);
-    } else if (epi == HL_EPI_LAGUERRE_STEP) {
+    } else if constexpr (EPI == HL_EPI_LAGUERRE_STEP) {
       // (-a + (2k+1) T_k - k T_{k-1}) / (k+1), in the reference's evaluation order
       Pack<V> a1 = ld_pack_coherent<V>(P.p1 + (int64_t)row * P.ld_p1 + col);
       Pack<V> a2 = ld_pack_coherent<V>(P.p2 + (int64_t)row * P.ld_p2 + col);
@@ -118,7 +103,7 @@ poly_spmm_kernel(const SpmmBatch b, const int32_t width, const int32_t G, const 
         t = __fsub_rn(t, __fmul_rn(c0, a2.v[i]));
         o.v[i] = __fdiv_rn(t, c2);
       }
-    } else if (epi == HL_EPI_CHEB_STEP) {
+    } else if constexpr (EPI == HL_EPI_CHEB_STEP) {
       Pack<V> a2 = ld_pack_coherent<V>(P.p2 + (int64_t)row * P.ld_p2 + col);
 #pragma unroll
       for (int i = 0; i < V; ++i) o.v[i] = __fsub_rn(__fmul_rn(2.f, acc[ch].v[i]), a2.v[i]);
@@ -145,6 +130,21 @@ poly_spmm_kernel(const SpmmBatch b, const int32_t width, const int32_t G, const 
   }
 }
 
+template <int V, int CH, int U>
+static void launch_epi(dim3 grid, cudaStream_t stream, const SpmmBatch& b, int32_t width, int G, int epi,
+                       float c0, float c1, float c2, float c3) {
+  switch (epi) {
+#define HL_EPI_CASE(E) \
+  case E: poly_spmm_kernel<V, CH, U, E><<<grid, kThreads, 0, stream>>>(b, width, G, c0, c1, c2, c3); break;
+    HL_EPI_CASE(HL_EPI_LAGUERRE_FIRST)
+    HL_EPI_CASE(HL_EPI_LAGUERRE_STEP)
+    HL_EPI_CASE(HL_EPI_CHEB_FIRST)
+    HL_EPI_CASE(HL_EPI_CHEB_STEP)
+    default: poly_spmm_kernel<V, CH, U, HL_EPI_LINCOMB><<<grid, kThreads, 0, stream>>>(b, width, G, c0, c1, c2, c3);
+#undef HL_EPI_CASE
+  }
+}
+
 static int launch_poly_spmm(const hl_spmm_problem* probs, int n, int32_t width, int epi, const float* c,
                             cudaStream_t stream) {
   if (!probs || n < 1 || n > HL_MAX_SPMM_PROBLEMS || width < 1) return HL_ERR_INVALID;
@@ -161,9 +161,12 @@ static int launch_poly_spmm(const hl_spmm_problem* probs, int n, int32_t width, 
     V = min(V, vec_for(P.p2, P.ld_p2, width, V));
     V = min(V, vec_for(P.p3, P.ld_p3, width, V));
   }
-  const int G = group_lanes(width, V);
+  // two vectors per lane whenever the row is wide enough to keep >= 4 lanes busy: halves the
+  // per-row index/address instruction overhead and every lane still reads full 128-byte lines
   const int chunks = (width + V - 1) / V;
-  const int CH = (chunks > G) ? 2 : 1;                     // up to 2 vectors per lane per column tile
+  const int CH = chunks >= 8 ? 2 : 1;
+  int G = 1;
+  while (G * CH < chunks && G < 32) G <<= 1;
   const int tile_w = G * V * CH;
   const int rows_per_block = kThreads / G;
 
@@ -183,12 +186,12 @@ static int launch_poly_spmm(const hl_spmm_problem* probs, int n, int32_t width, 
     const float k = c0;
     c0 = k; c1 = 2.f * k + 1.f; c2 = k + 1.f;
   }
-#define HL_SPMM_CASE(VV, CC) \
-  poly_spmm_kernel<VV, CC><<<grid, kThreads, 0, stream>>>(b, width, G, epi, c0, c1, c2, c3)
-  if (V == 4) { if (CH == 2) HL_SPMM_CASE(4, 2); else HL_SPMM_CASE(4, 1); }
-  else if (V == 2) { if (CH == 2) HL_SPMM_CASE(2, 2); else HL_SPMM_CASE(2, 1); }
-  else { if (CH == 2) HL_SPMM_CASE(1, 2); else HL_SPMM_CASE(1, 1); }
-#undef HL_SPMM_CASE
+  if (V == 4) { if (CH == 2) launch_epi<4, 2, 2>(grid, stream, b, width, G, epi, c0, c1, c2, c3);
+                else launch_epi<4, 1, 4>(grid, stream, b, width, G, epi, c0, c1, c2, c3); }
+  else if (V == 2) { if (CH == 2) launch_epi<2, 2, 4>(grid, stream, b, width, G, epi, c0, c1, c2, c3);
+                     else launch_epi<2, 1, 4>(grid, stream, b, width, G, epi, c0, c1, c2, c3); }
+  else { if (CH == 2) launch_epi<1, 2, 4>(grid, stream, b, width, G, epi, c0, c1, c2, c3);
+         else launch_epi<1, 1, 4>(grid, stream, b, width, G, epi, c0, c1, c2, c3); }
   HL_LAUNCH_CHECK("poly_spmm_kernel");
   return HL_OK;
 }

@@ -216,7 +216,7 @@ class NodeEdgeInt(nn.Module):
             return "relu"
         return None
 
-    def forward(self, x_t, x_s, par, D):
+    def forward(self, x_t, x_s, par, D, nvalid=(None, None)):
         inc = _incidence_of(par)
         x_s2t = F_hl.edge_to_node(x_s, D, inc)
         x_t2s = F_hl.node_to_edge(x_t, inc)
@@ -228,42 +228,47 @@ class NodeEdgeInt(nn.Module):
             a_t = F_hl.att_gate(self.WQ_Edge(x_s2t), self.WQ_Node(x_t), k_t, self.lambda_Node, name)
             a_s = F_hl.att_gate(self.WQ_Node(x_t2s), self.WQ_Edge(x_s), k_s, self.lambda_Edge, name)
             return a_t, a_s
-        x_t1 = _mlp(self.WV_Node, x_s2t, x_t)
-        x_s1 = _mlp(self.WV_Edge, x_t2s, x_s)
+        x_t1 = _mlp(self.WV_Node, x_s2t, x_t, nvalid[0])
+        x_s1 = _mlp(self.WV_Edge, x_t2s, x_s, nvalid[1])
         return x_t1, x_s1
 
 
 MSI = NodeEdgeInt
 
 
-def _bn_relu(bn, x, slope=0.0):
+def _bn_relu(bn, x, slope=0.0, nvalid=None):
     """nn.BatchNorm1d (+ReLU) through the fused kernels in training mode; running statistics updated
-    exactly like torch (momentum, unbiased variance)."""
+    exactly like torch (momentum, unbiased variance).  `nvalid` (device int32 scalar) marks the rows
+    beyond it as padding of a fixed-capacity batch."""
     if not (bn.training or not bn.track_running_stats):
         y = torch.nn.functional.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
         return torch.nn.functional.leaky_relu(y, slope) if slope != 1.0 else y
-    y, stats = F_hl.bn_act_train(x, bn.weight, bn.bias, bn.eps, slope)
+    y, stats = F_hl.bn_act_train(x, bn.weight, bn.bias, bn.eps, slope, nvalid)
     if bn.track_running_stats and bn.training:
         with torch.no_grad():
             f = x.shape[1]
-            n = x.shape[0]
             bn.num_batches_tracked += 1
             m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
             bn.running_mean.mul_(1 - m).add_(stats[:f], alpha=m)
-            bn.running_var.mul_(1 - m).add_(stats[f:], alpha=m * n / max(n - 1, 1))
+            if nvalid is None:
+                n = x.shape[0]
+                bn.running_var.mul_(1 - m).add_(stats[f:], alpha=m * n / max(n - 1, 1))
+            else:
+                nf = nvalid.to(torch.float32)
+                bn.running_var.mul_(1 - m).add_(stats[f:] * (m * nf / (nf - 1).clamp(min=1)))
     return y
 
 
-def _mlp(seq, transferred, own):
+def _mlp(seq, transferred, own, nvalid=None):
     """Linear(cat[transferred, own]) -> BN -> ReLU -> Linear -> BN -> ReLU without materialising the
     concat: the first Linear is split over its two column blocks (lib/Hodge_Cheb_Conv.py:307-308)."""
     lin0, bn0, _, lin1, bn1, _ = seq
     d = transferred.shape[1]
     h = torch.addmm(lin0.bias, transferred, lin0.weight[:, :d].t())
     h = h.addmm(own, lin0.weight[:, d:].t())
-    h = _bn_relu(bn0, h)
+    h = _bn_relu(bn0, h, 0.0, nvalid)
     h = torch.addmm(lin1.bias, h, lin1.weight.t())
-    return _bn_relu(bn1, h)
+    return _bn_relu(bn1, h, 0.0, nvalid)
 
 
 class GraphBatchNorm(nn.Module):
@@ -277,8 +282,8 @@ class GraphBatchNorm(nn.Module):
     def forward(self, x):
         return _bn_relu(self.module, x, slope=1.0)
 
-    def forward_act(self, x, slope=0.0):
-        return _bn_relu(self.module, x, slope=slope)
+    def forward_act(self, x, slope=0.0, nvalid=None):
+        return _bn_relu(self.module, x, slope, nvalid)
 
 
 class NEConv(nn.Module):
@@ -294,9 +299,9 @@ class NEConv(nn.Module):
         self.module_5 = GraphBatchNorm(fout)
         self.slope, self.p = slope, dropout_ratio
 
-    def forward(self, x_t, edge_index_t, edge_weight_t, x_s, edge_index_s, edge_weight_s):
-        x_t = self.module_1.forward_act(self.module_0(x_t, edge_index_t, edge_weight_t), self.slope)
-        x_s = self.module_5.forward_act(self.module_4(x_s, edge_index_s, edge_weight_s), self.slope)
+    def forward(self, x_t, edge_index_t, edge_weight_t, x_s, edge_index_s, edge_weight_s, nvalid=(None, None)):
+        x_t = self.module_1.forward_act(self.module_0(x_t, edge_index_t, edge_weight_t), self.slope, nvalid[0])
+        x_s = self.module_5.forward_act(self.module_4(x_s, edge_index_s, edge_weight_s), self.slope, nvalid[1])
         if self.p > 0.0:
             x_t = torch.nn.functional.dropout(x_t, self.p, self.training)
             x_s = torch.nn.functional.dropout(x_s, self.p, self.training)

@@ -13,9 +13,9 @@ class _MlpBlock(nn.Sequential):
     """nn.Sequential(Linear, BatchNorm1d, ReLU, Dropout) of lib/Hodge_ST_Model.py:596-601 with the
     BN+ReLU pair routed through the fused kernel."""
 
-    def forward(self, x):
+    def forward(self, x, nvalid=None):
         lin, bn, _, drop = self
-        return drop(_bn_relu(bn, lin(x)))
+        return drop(_bn_relu(bn, lin(x), 0.0, nvalid))
 
 
 class HL_HGCNN_zinc_dense_int3_pyr(nn.Module):
@@ -47,24 +47,29 @@ class HL_HGCNN_zinc_dense_int3_pyr(nn.Module):
     def forward(self, data, device="cuda:0", if_final_layer=False):
         x_s, x_t = data.x_s, data.x_t
         n, e = x_t.shape[0], x_s.shape[0]
+        # fixed-capacity (CUDA-graph) batches carry device-side valid counts; rows beyond are padding
+        nv = (getattr(data, "n_valid_nodes", None), getattr(data, "n_valid_edges", None))
+        nv_g = getattr(data, "n_valid_graphs", None)
         # operators are bucketed once per batch; every layer below reuses the CSR tables
         op_t = operator_for(data.edge_index_t, data.edge_weight_t, n)
         op_s = operator_for(data.edge_index_s, data.edge_weight_s, e)
         seg_t = F_hl.Segments.from_counts(torch.as_tensor(data.num_node1, device=x_t.device))
         seg_s = F_hl.Segments.from_counts(torch.as_tensor(data.num_edge1, device=x_t.device))
-        x_t, x_s = self.HL_init_conv(x_t, op_t, None, x_s, op_s, None)
+        x_t, x_s = self.HL_init_conv(x_t, op_t, None, x_s, op_s, None, nv)
         x_s0, x_t0 = x_s, x_t
         inc = incidence_for(data.edge_index, n)
-        D = inc.degree()                    # = degree(edge_index.view(-1)) of :624 (no 1e-6 in this model)
+        D = getattr(data, "D", None)
+        if D is None:
+            D = inc.degree()                # = degree(edge_index.view(-1)) of :624 (no 1e-6 in this model)
         for i, _ in enumerate(self.channels):
             for j in range(self.channels[i]):
-                x_t, x_s = getattr(self, f"NEInt{i}{j}")(x_t0, x_s0, inc, D)
-                x_t, x_s = getattr(self, f"NEConv{i}{j}")(x_t, op_t, None, x_s, op_s, None)
+                x_t, x_s = getattr(self, f"NEInt{i}{j}")(x_t0, x_s0, inc, D, nv)
+                x_t, x_s = getattr(self, f"NEConv{i}{j}")(x_t, op_t, None, x_s, op_s, None, nv)
                 x_t0 = torch.cat([x_t0, x_t], dim=-1)
                 x_s0 = torch.cat([x_s0, x_s], dim=-1)
         x = torch.cat((F_hl.segment_mean(x_s, seg_s), F_hl.segment_mean(x_t, seg_t)), -1)
         for i, _ in enumerate(self.mlp_channels):
-            x = getattr(self, "mlp%d" % i)(x)
+            x = getattr(self, "mlp%d" % i)(x, nv_g)
         if if_final_layer:
             return x, self.out(x)
         return self.out(x)

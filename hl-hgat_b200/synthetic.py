@@ -89,7 +89,7 @@ def make_batch(shape="zinc", batch_size=128, seed=0, node_dim=None, edge_dim=Non
     gen = torch.Generator().manual_seed(seed)
     b = SimpleNamespace()
     for k, v in cols.items():
-        arr = np.concatenate(v, axis=-1)
+        arr = np.ascontiguousarray(np.concatenate(v, axis=-1))
         setattr(b, k, torch.from_numpy(arr))
     b.x_t = torch.randn(n_off, nd, generator=gen)
     b.x_s = torch.randn(e_off, ed, generator=gen)

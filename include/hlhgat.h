@@ -41,6 +41,8 @@ int hl_version(void);
 const char* hl_status_string(int status);
 const char* hl_last_cuda_error(void);
 int hl_device_sm_count(void);
+/* number of kernels this library has launched in this process (host-side counter) */
+unsigned long long hl_launch_count(void);
 
 /* --------------------------------------------------------------------------------------------
  * CSR construction from a COO edge list (once per mini-batch and operator).
@@ -196,16 +198,19 @@ int hl_att_gate_bwd(const float* qc, const float* qs, const float* k, const floa
  * lib/Hodge_Cheb_Conv.py:278-282, and torch.cat lib/Hodge_ST_Model.py:632-633.
  *   y = act( (x - mean) * rsqrt(var_biased + eps) * gamma + beta ),  act: slope 0 = ReLU, 1 = identity
  * stats[0:F] = mean, stats[F:2F] = biased var (both fp32).  running stats are the caller's.
+ * `nvalid` (device int32, nullable): only rows [0, *nvalid) enter the statistics; rows beyond are
+ * padding ("ghost" rows of a fixed-capacity batch replayed from a CUDA graph): y and dx are written
+ * as exact zeros there, so they contribute nothing to any later reduction or weight gradient.
  * -------------------------------------------------------------------------------------------- */
 size_t hl_bn_workspace(int32_t nrows, int32_t width);
 int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_t width,
                   const float* gamma, const float* beta, float eps, float slope,
-                  float* y, int64_t ld_y, float* stats, void* workspace, size_t workspace_bytes,
-                  hl_stream_t stream);
+                  float* y, int64_t ld_y, float* stats, const int32_t* nvalid /* device, nullable */,
+                  void* workspace, size_t workspace_bytes, hl_stream_t stream);
 int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64_t ld_y,
                   const float* dy, int64_t ld_dy, int32_t nrows, int32_t width,
                   const float* gamma, const float* stats, float eps, float slope,
-                  float* dx, int64_t ld_dx, float* dgamma, float* dbeta,
+                  float* dx, int64_t ld_dx, float* dgamma, float* dbeta, const int32_t* nvalid,
                   void* workspace, size_t workspace_bytes, hl_stream_t stream);
 
 #ifdef __cplusplus

@@ -302,9 +302,12 @@ def test_zinc_model_full_size_vs_oracle():
         if r is None:
             assert a is None, n
             continue
-        err = (a.cpu() - r).norm() / (r.norm() + 1e-12)
-        worst = max(worst, float(err))
-        assert err < 1e-3, (n, float(err))
+        # biases feeding a BatchNorm have an exactly-zero true gradient (pure rounding noise in
+        # both implementations): relative bar with an absolute floor
+        diff, scale = float((a.cpu() - r).norm()), float(r.norm())
+        assert diff < 1e-3 * scale + 1e-7 * r.numel() ** 0.5, (n, diff, scale)
+        if scale > 1e-6:
+            worst = max(worst, diff / scale)
     print("worst relative grad error", worst)
 
 
