@@ -196,21 +196,25 @@ def run_ours(args, world, rank, local):
     model = HL_HGCNN_zinc_dense_int3_pyr(**MODEL_CTOR).to(dev).train()
     broadcast_parameters(model)
     bucket = FlatGradBucket(model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3, fused=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3, fused=True, capturable=True)
     crit = torch.nn.L1Loss()
 
-    host = [pin_batch(make_batch("zinc", BATCH, seed=1000 * rank + i)) for i in range(POOL)]
-    resident = [batch_to(b, dev) for b in host]
-    h2d_bytes = batch_nbytes(host[0])
+    from hlhgat_b200.training import Capacity, pad_batch, padded_nbytes, GraphedTrainStep, StaticBatch
+    raw = [make_batch("zinc", BATCH, seed=1000 * rank + i) for i in range(POOL)]
+    cap = Capacity.covering(raw)
+    if world > 1:                                        # same capacity on every rank (same graph shapes)
+        t = torch.tensor([cap.nodes, cap.edges, cap.nnz_t, cap.nnz_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cap.nodes, cap.edges, cap.nnz_t, cap.nnz_s = (int(v) for v in t.tolist())
+    host = [pad_batch(b, cap, pin=True) for b in raw]    # pinned host buffers in the reference's batch format
+    h2d_bytes = padded_nbytes(host[0])
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-
-    def train_step(b):
-        bucket.zero()
-        loss = crit(model(b, device=dev), b.y)
-        loss.backward()
-        bucket.all_reduce_mean()
-        opt.step()
-        return loss
+    stepper = GraphedTrainStep(model, crit, opt, bucket, host[0], dev, warmup=3)
+    resident = []
+    for b in host:
+        stepper.batch.load(b)
+        resident.append(stepper.batch.clone_resident())
+    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -220,7 +224,6 @@ def run_ours(args, world, rank, local):
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = N.lib().hl_launch_count()
         e0.record()
         for i in range(steps):
             fn(i)
@@ -231,26 +234,28 @@ def run_ours(args, world, rank, local):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t)
-        return ms, N.lib().hl_launch_count() - l0
+        return ms
 
-    def step_resident(i):
-        train_step(resident[i % POOL])
+    def step_resident(i):                                # inputs already in HBM: D2D into the graph's static buffers
+        stepper.batch.load(resident[i % POOL])
+        stepper.step()
 
-    def step_e2e(i):
-        clear_caches()                                   # a fresh batch: CSR tables are rebuilt from the COO
-        b = batch_to(host[i % POOL], dev, non_blocking=True)
-        loss = train_step(b)
-        loss_host.copy_(loss.detach(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()        # the user reads the loss every step
+    def step_e2e(i):                                     # host buffers in, loss out, every step
+        stepper.batch.load(host[i % POOL], non_blocking=True)
+        loss = stepper.step()
+        loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
 
     for i in range(args.warmup):
         step_resident(i)
     sampler = ClockSampler(local) if rank == 0 else None
-    ms, launches = timed(step_resident, args.steps)
+    ms = timed(step_resident, args.steps)
     clocks = sampler.stop() if sampler else None
-    for i in range(max(2, args.warmup // 2)):
+    for i in range(args.warmup):
         step_e2e(i)
-    ms_e2e, _ = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, args.steps)
+    launches = stepper.launches_per_step * args.steps
+    final_loss = float(loss_host)
 
     value = BATCH * world * args.steps / (ms * 1e-3)
     e2e = BATCH * world * args.steps / (ms_e2e * 1e-3)
@@ -263,12 +268,15 @@ def run_ours(args, world, rank, local):
                        "parallelism": f"dp{world}", "batch_pool": POOL,
                        "l2": "no explicit flush: per-step working set (activations saved for backward, ~1 GB) exceeds the 126 MB L2 "
                              "and consecutive steps use different batches",
+                       "execution": "whole step (CSR bucketing + forward + backward) replayed as one CUDA graph on batches padded "
+                                    f"to a fixed capacity ({cap.nodes} nodes / {cap.edges} edges, ~2% ghost rows), then all-reduce + fused Adam graph",
                        "gemm": "dense Theta/MLP GEMMs via cuBLAS fp32 (torch.mm); all sparse/segment/BN kernels hand-written"},
             "e2e": {"value": e2e, "unit": "graphs/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches), "clocks": clocks}
+            "gpu_launches": int(launches), "gpu_launches_note": "libhlhgat kernels inside the replayed graph x steps (cuBLAS/ATen launches not counted)",
+            "final_loss": final_loss, "clocks": clocks}
     try:
-        line["roofline"] = spmm_roofline(dev, resident[0])
+        line["roofline"] = spmm_roofline(dev, batch_to(raw[0], dev))
     except Exception as exc:  # pragma: no cover
         line["roofline"] = {"error": repr(exc)}
     if world == 1 and not args.no_cpu_baseline:

@@ -49,6 +49,13 @@ _SIGNATURES = {
     "hl_owner_gather": (C.c_int, [_vp, _i32, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i32, _vp]),
     "hl_att_gate_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _f32, C.c_int, _vp, _vp]),
     "hl_att_gate_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, C.c_int, _vp, _vp, _vp, _vp]),
+    "hl_build_edges_workspace": (_sz, [_i64]),
+    "hl_build_edges": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hl_lambda_max_workspace": (_sz, [_i32, _i32, _i32]),
+    "hl_lambda_max": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "hl_laplacian_rowptr_workspace": (_sz, [_i32, _i32]),
+    "hl_laplacian_rowptr": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hl_laplacian_fill": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hl_bn_workspace": (_sz, [_i32, _i32]),
     "hl_bn_act_fwd": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "hl_bn_act_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32,

@@ -1,7 +1,7 @@
 // Training-mode BatchNorm over rows fused with the activation and with the strided store into the
 // dense-connection buffer (hl_bn_act_fwd / hl_bn_act_bwd).  Deterministic two-stage column
-// reductions: per-block shifted sums (numerically the "shifted data" variance algorithm), merged
-// in fp64 in a fixed order.  No atomics.
+// reductions: per-block sums of (x - x[0,col]) and its square (the "shifted data" variance algorithm,
+// shift = first row), merged in fp64 in a fixed order by one warp per column.  No atomics.
 #include "common.cuh"
 
 namespace hl {
@@ -12,7 +12,7 @@ constexpr int kBnRowsPerBlock = 128;
 
 static inline int bn_row_blocks(int32_t nrows) { return (nrows + kBnRowsPerBlock - 1) / kBnRowsPerBlock; }
 
-// partial[(blk * 2 + {0,1}) * width + col] = {mean_b, M2_b} of the block's rows (fp64)
+// partial[(blk * 2 + {0,1}) * width + col] = {sum (x - x[0,col]), sum (x - x[0,col])^2} over the block's rows (fp64)
 template <int V>
 __global__ void __launch_bounds__(kBnThreads)
 bn_stats_partial_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows_cap, const int32_t* __restrict__ nvalid,
@@ -28,7 +28,7 @@ bn_stats_partial_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows
 #pragma unroll
   for (int i = 0; i < V; ++i) shift.v[i] = s1.v[i] = s2.v[i] = 0.f;
   if (act && r0 < r1) {
-    shift = ld_pack<V>(x + (int64_t)r0 * ld_x + col);
+    shift = ld_pack<V>(x + col);                             // common shift: row 0 of every column
     for (int r = r0 + warp; r < r1; r += kBnWarps) {
       Pack<V> v = ld_pack<V>(x + (int64_t)r * ld_x + col);
 #pragma unroll
@@ -46,7 +46,6 @@ bn_stats_partial_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows
   }
   __syncthreads();
   if (warp == 0 && act) {
-    const double n = (double)max(r1 - r0, 1);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       double a = 0.0, b = 0.0;
@@ -55,31 +54,44 @@ bn_stats_partial_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows
         a += (double)sh[0][w][lane * V + i];
         b += (double)sh[1][w][lane * V + i];
       }
-      partial[((int64_t)blockIdx.x * 2 + 0) * width + col + i] = (double)shift.v[i] + a / n;
-      partial[((int64_t)blockIdx.x * 2 + 1) * width + col + i] = b - a * a / n;
+      partial[((int64_t)blockIdx.x * 2 + 0) * width + col + i] = a;
+      partial[((int64_t)blockIdx.x * 2 + 1) * width + col + i] = b;
     }
   }
 }
 
-__global__ void bn_stats_final_kernel(const double* __restrict__ partial, int nblk, int32_t nrows_cap,
-                                      const int32_t* __restrict__ nvalid, int32_t width, float* __restrict__ stats) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per column: lanes stride over the row blocks, fixed-order shuffle tree
+__device__ __forceinline__ void warp_sum2(double& a, double& b) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, off);
+    b += __shfl_xor_sync(0xffffffffu, b, off);
+  }
+}
+
+__global__ void bn_stats_final_kernel(const double* __restrict__ partial, int nblk, const float* __restrict__ x,
+                                      int32_t nrows_cap, const int32_t* __restrict__ nvalid, int32_t width,
+                                      float* __restrict__ stats) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= width) return;
   const int32_t nrows = nvalid ? min(__ldg(nvalid), nrows_cap) : nrows_cap;
-  double n = 0.0, mean = 0.0, m2 = 0.0;
-  for (int b = 0; b < nblk; ++b) {                            // Chan et al. pairwise merge, fixed order
-    const double nb = (double)(min((b + 1) * kBnRowsPerBlock, nrows) - b * kBnRowsPerBlock);
-    if (nb <= 0.0) break;
-    const double mb = partial[((int64_t)b * 2 + 0) * width + c];
-    const double qb = partial[((int64_t)b * 2 + 1) * width + c];
-    const double tot = n + nb;
-    const double delta = mb - mean;
-    mean += delta * nb / tot;
-    m2 += qb + delta * delta * n * nb / tot;
-    n = tot;
+  double a = 0.0, b = 0.0;
+  for (int k = lane; k < nblk; k += 32) {
+    a += partial[((int64_t)k * 2 + 0) * width + c];
+    b += partial[((int64_t)k * 2 + 1) * width + c];
   }
-  stats[c] = (float)mean;
-  stats[width + c] = n > 0.0 ? (float)(m2 / n) : 0.f;
+  warp_sum2(a, b);
+  if (lane == 0) {
+    if (nrows > 0) {
+      const double n = (double)nrows, m = a / n;
+      stats[c] = (float)((double)__ldg(x + c) + m);
+      stats[width + c] = (float)fmax(b / n - m * m, 0.0);
+    } else {
+      stats[c] = 0.f;
+      stats[width + c] = 0.f;
+    }
+  }
 }
 
 template <int V>
@@ -170,20 +182,24 @@ bn_bwd_partial_kernel(const float* __restrict__ x, int64_t ld_x, const float* __
   }
 }
 
-// sums[0:F] = sum dz (= dbeta), sums[F:2F] = sum dz*xhat (= dgamma)
+// sums[0:F] = sum dz (= dbeta), sums[F:2F] = sum dz*xhat (= dgamma); one warp per column
 __global__ void bn_bwd_final_kernel(const double* __restrict__ partial, int nblk, int32_t width,
                                     float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= width) return;
   double a = 0.0, b = 0.0;
-  for (int k = 0; k < nblk; ++k) {
+  for (int k = lane; k < nblk; k += 32) {
     a += partial[((int64_t)k * 2 + 0) * width + c];
     b += partial[((int64_t)k * 2 + 1) * width + c];
   }
-  sums[c] = (float)a;
-  sums[width + c] = (float)b;
-  if (dbeta) dbeta[c] = (float)a;
-  if (dgamma) dgamma[c] = (float)b;
+  warp_sum2(a, b);
+  if (lane == 0) {
+    sums[c] = (float)a;
+    sums[width + c] = (float)b;
+    if (dbeta) dbeta[c] = (float)a;
+    if (dgamma) dgamma[c] = (float)b;
+  }
 }
 
 template <int V>
@@ -253,7 +269,7 @@ extern "C" int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_
   else if (V == 2) bn_stats_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
   else bn_stats_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
   HL_LAUNCH_CHECK("bn_stats_partial_kernel");
-  bn_stats_final_kernel<<<(width + 127) / 128, 128, 0, st>>>(partial, nblk, nrows, nvalid, width, stats);
+  bn_stats_final_kernel<<<(width * 32 + 255) / 256, 256, 0, st>>>(partial, nblk, x, nrows, nvalid, width, stats);
   HL_LAUNCH_CHECK("bn_stats_final_kernel");
   const int g = ew_grid((int64_t)nrows * (width / V));
   if (V == 4) bn_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
@@ -285,7 +301,7 @@ extern "C" int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64
   else if (V == 2) bn_bwd_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
   else bn_bwd_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
   HL_LAUNCH_CHECK("bn_bwd_partial_kernel");
-  bn_bwd_final_kernel<<<(width + 127) / 128, 128, 0, st>>>(partial, nblk, width, sums, dgamma, dbeta);
+  bn_bwd_final_kernel<<<(width * 32 + 255) / 256, 256, 0, st>>>(partial, nblk, width, sums, dgamma, dbeta);
   HL_LAUNCH_CHECK("bn_bwd_final_kernel");
   const int g = ew_grid((int64_t)nrows * (width / V));
   if (V == 4) bn_bwd_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx);

@@ -251,12 +251,14 @@ class Segments:
         return cls(rowptr, members, owner, nrows, idx.numel())
 
     @classmethod
-    def from_counts(cls, counts):
-        """Contiguous segments (sorted `batch` vector): counts[g] rows per graph."""
+    def from_counts(cls, counts, total=None):
+        """Contiguous segments (sorted `batch` vector): counts[g] rows per graph.  Pass `total`
+        (= counts.sum(), known on the host) to stay free of device->host syncs (CUDA-graph capture)."""
         counts = counts.to(torch.int64)
         ptr = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=counts.device)
         ptr[1:] = torch.cumsum(counts, 0)
-        owner = torch.repeat_interleave(torch.arange(counts.numel(), device=counts.device, dtype=torch.int32), counts)
+        ids = torch.arange(counts.numel(), device=counts.device, dtype=torch.int32)
+        owner = torch.repeat_interleave(ids, counts, output_size=total)
         return cls(ptr, None, owner, counts.numel(), int(owner.numel()))
 
 

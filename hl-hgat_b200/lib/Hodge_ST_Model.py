@@ -53,8 +53,8 @@ class HL_HGCNN_zinc_dense_int3_pyr(nn.Module):
         # operators are bucketed once per batch; every layer below reuses the CSR tables
         op_t = operator_for(data.edge_index_t, data.edge_weight_t, n)
         op_s = operator_for(data.edge_index_s, data.edge_weight_s, e)
-        seg_t = F_hl.Segments.from_counts(torch.as_tensor(data.num_node1, device=x_t.device))
-        seg_s = F_hl.Segments.from_counts(torch.as_tensor(data.num_edge1, device=x_t.device))
+        seg_t = F_hl.Segments.from_counts(torch.as_tensor(data.num_node1, device=x_t.device), total=n)
+        seg_s = F_hl.Segments.from_counts(torch.as_tensor(data.num_edge1, device=x_t.device), total=e)
         x_t, x_s = self.HL_init_conv(x_t, op_t, None, x_s, op_s, None, nv)
         x_s0, x_t0 = x_s, x_t
         inc = incidence_for(data.edge_index, n)

@@ -60,6 +60,17 @@ class CsrOperator:
         self._ei, self._ew = edge_index, edge_weight
         self._fwd = self._bwd = None
 
+    @classmethod
+    def from_csr(cls, rowptr, colidx, vals, nrows, symmetric=True, transpose=None):
+        """Wrap CSR tables built on the device (hl_laplacian_fill): for a symmetric operator the same
+        tables serve the forward and the adjoint pass."""
+        op = cls.__new__(cls)
+        op.nrows, op.nnz = int(nrows), int(colidx.numel())
+        op._ei = op._ew = None
+        op._fwd = (rowptr, colidx, vals)
+        op._bwd = op._fwd if symmetric else transpose
+        return op
+
     @property
     def fwd(self):
         if self._fwd is None:
@@ -86,6 +97,13 @@ class Incidence:
         ar = torch.arange(e, dtype=torch.int64, device=ei.device)
         self.rowptr, self.edge, _, _ = csr_from_coo(ei.reshape(-1), torch.cat([ar, ar]), None,
                                                     self.num_nodes, tie=N.HL_TIE_COLUMN)
+
+    @classmethod
+    def from_tables(cls, tail, head, rowptr, edge, num_nodes):
+        inc = cls.__new__(cls)
+        inc.num_nodes, inc.num_edges = int(num_nodes), int(tail.numel())
+        inc.tail, inc.head, inc.rowptr, inc.edge = tail, head, rowptr, edge
+        return inc
 
     def degree(self):
         return (self.rowptr[1:] - self.rowptr[:-1]).to(torch.float32)

@@ -213,6 +213,50 @@ int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64_t ld_y,
                   float* dx, int64_t ld_dx, float* dgamma, float* dbeta, const int32_t* nvalid,
                   void* workspace, size_t workspace_bytes, hl_stream_t stream);
 
+/* --------------------------------------------------------------------------------------------
+ * Simplex-graph construction for a whole mini-batch (block-diagonal), on the GPU.
+ * Replaces: Dataset.process lib/Hodge_Dataset.py:447-456,467-468 (to_undirected -> i<j ->
+ * dense B1 -> B1 B1^T -> eigh -> 2L/lambda_max -> dense_to_sparse), the same tail of MLGC
+ * (:276-288) and the block-diagonal collation of PairData.__inc__ (:40-48): the caller passes the
+ * directed edges of ALL graphs with global (graph-contiguous) node ids.
+ *
+ * step 1  hl_build_edges: directed (any order, duplicates and both directions allowed) -> unique
+ *         undirected i<j edges in lexicographic order (= to_undirected + mask, :447-450).
+ *         tail/head/attr_out need room for n_directed entries; *n_edges_out (device) = count.
+ *         attr (optional int64 per directed edge) is min-reduced over duplicates (reduce='min').
+ * step 2  node -> incident-edge CSR: hl_csr_from_coo(row = [tail | head], col = [e | e],
+ *         tie = HL_TIE_COLUMN)  (rowptr diff = node degree).
+ * step 3  hl_lambda_max: lambda_max(B1 B1^T) per graph, Lanczos with full re-orthogonalisation in
+ *         fp64, one CTA per graph, at most min(n_g, max_steps) steps (exact when max_steps >=
+ *         n_g); last_change[g] = |theta_m - theta_{m-1}| of the final step (convergence evidence).
+ * step 4  hl_laplacian_rowptr (row counts + scan; nnz = rowptr[last]) then hl_laplacian_fill:
+ *         CSR of L0 = 2 B1 B1^T / lmax (row i: ascending neighbours, diagonal = degree; isolated
+ *         node = empty row) and L1 = 2 B1^T B1 / lmax (row e: ascending union of the edges
+ *         incident to its endpoints; +1 if both edges leave / both enter the shared node, else -1;
+ *         diagonal 2), values = fp32(2*m)/lmax[graph] as the reference computes them.  Column
+ *         order equals the reference's row-major dense_to_sparse COO, so (rowptr, col, val) is at
+ *         once the forward and (L symmetric) the transposed operator for hl_poly_*.
+ * -------------------------------------------------------------------------------------------- */
+size_t hl_build_edges_workspace(int64_t n_directed);
+int hl_build_edges(const int64_t* src, const int64_t* dst, int64_t n_directed, int64_t n_nodes,
+                   const int64_t* attr, int32_t* tail, int32_t* head, int64_t* attr_out,
+                   int32_t* n_edges_out, void* workspace, size_t workspace_bytes, hl_stream_t stream);
+size_t hl_lambda_max_workspace(int32_t n_graphs, int32_t max_nodes, int32_t max_steps);
+int hl_lambda_max(const int32_t* node_ptr /* [G+1] */, int32_t n_graphs, int32_t max_nodes,
+                  const int32_t* inc_rowptr, const int32_t* inc_edge,
+                  const int32_t* tail, const int32_t* head, int32_t max_steps,
+                  float* lambda_max, float* last_change, void* workspace, size_t workspace_bytes,
+                  hl_stream_t stream);
+size_t hl_laplacian_rowptr_workspace(int32_t n_edges, int32_t n_nodes);
+int hl_laplacian_rowptr(const int32_t* tail, const int32_t* head, int32_t n_edges, int32_t n_nodes,
+                        const int32_t* inc_rowptr, int32_t* l0_rowptr /* [N+1] */, int32_t* l1_rowptr /* [E+1] */,
+                        void* workspace, size_t workspace_bytes, hl_stream_t stream);
+int hl_laplacian_fill(const int32_t* tail, const int32_t* head, int32_t n_edges, int32_t n_nodes,
+                      const int32_t* inc_rowptr, const int32_t* inc_edge,
+                      const int32_t* node_graph, const float* lambda_max /* per graph */,
+                      const int32_t* l0_rowptr, int32_t* l0_col, float* l0_val,
+                      const int32_t* l1_rowptr, int32_t* l1_col, float* l1_val, hl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -279,7 +279,9 @@ def test_zinc_model_vs_golden_reference(K):
 
 def test_zinc_model_full_size_vs_oracle():
     """BASELINE config-1 model (filters 64/128/256, K=2) on a 64-graph ZINC-shaped batch: forward
-    and all parameter gradients against the CPU oracle."""
+    and all parameter gradients against the CPU oracle.  The bar is rtol 1e-4 on the prediction and,
+    for gradients (which pass through 38 training-mode BatchNorms in fp32), "as close to the fp64
+    oracle as the fp32 oracle itself is" -- the fp32 CPU reference carries the same rounding noise."""
     from hlhgat_b200.lib.Hodge_ST_Model import HL_HGCNN_zinc_dense_int3_pyr
     torch.manual_seed(0)
     ctor = dict(channels=[2, 2, 2], filters=[64, 128, 256], mlp_channels=[], K=2, node_dim=21, edge_dim=3, keig=7)
@@ -287,28 +289,33 @@ def test_zinc_model_full_size_vs_oracle():
     ref.train()
     b = make_batch("zinc", 64, seed=11)
     pred_ref = ref(b)
-    loss_ref = torch.nn.functional.l1_loss(pred_ref, b.y)
-    g_ref = torch.autograd.grad(loss_ref, list(ref.parameters()), allow_unused=True)
+    g_ref = torch.autograd.grad(torch.nn.functional.l1_loss(pred_ref, b.y), list(ref.parameters()), allow_unused=True)
+    import copy
+    ref64 = copy.deepcopy(ref).double()
+    b64 = copy.copy(b)
+    for k in ("x_t", "x_s", "y", "edge_weight_t", "edge_weight_s"):
+        setattr(b64, k, getattr(b, k).double())
+    g64 = torch.autograd.grad(torch.nn.functional.l1_loss(ref64(b64), b64.y), list(ref64.parameters()), allow_unused=True)
     model = HL_HGCNN_zinc_dense_int3_pyr(**ctor).to(DEV)
     model.load_state_dict(ref.state_dict(), strict=True)
     model.train()
     d = batch_to(b, DEV)
     pred = model(d, device=DEV)
     close(pred, pred_ref, rtol=1e-4, atol=1e-4)
-    loss = torch.nn.functional.l1_loss(pred, d.y)
-    g = torch.autograd.grad(loss, list(model.parameters()), allow_unused=True)
+    g = torch.autograd.grad(torch.nn.functional.l1_loss(pred, d.y), list(model.parameters()), allow_unused=True)
     worst = 0.0
-    for (n, _), a, r in zip(model.named_parameters(), g, g_ref):
+    for (n, _), a, r, r64 in zip(model.named_parameters(), g, g_ref, g64):
         if r is None:
             assert a is None, n
             continue
-        # biases feeding a BatchNorm have an exactly-zero true gradient (pure rounding noise in
-        # both implementations): relative bar with an absolute floor
-        diff, scale = float((a.cpu() - r).norm()), float(r.norm())
-        assert diff < 1e-3 * scale + 1e-7 * r.numel() ** 0.5, (n, diff, scale)
+        scale = float(r64.norm())
+        ours = float((a.cpu().double() - r64).norm())
+        cpu32 = float((r.double() - r64).norm())
+        floor = 1e-7 * r.numel() ** 0.5          # biases feeding a BatchNorm: exactly-zero true gradient
+        assert ours < max(1e-4 * scale, 3.0 * cpu32) + floor, (n, ours, cpu32, scale)
         if scale > 1e-6:
-            worst = max(worst, diff / scale)
-    print("worst relative grad error", worst)
+            worst = max(worst, ours / scale)
+    print("worst relative grad error vs fp64 oracle", worst)
 
 
 def test_determinism_two_runs_bit_identical():
