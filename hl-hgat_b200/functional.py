@@ -48,6 +48,74 @@ def poly_basis_bwd(family, K, ops, g0s, gts, width):
         N.check(L.hl_poly_basis_bwd(family, K, sides, len(ops), width, N.stream_ptr()), "hl_poly_basis_bwd")
 
 
+def wgrad(g, x, out=None):
+    """dW[Fo,Fi] = g[R,Fo]^T x[R,Fi] (deterministic split-row reduction); `out` may be a column slice."""
+    L = N.lib()
+    g, ldg = N.row_major(g)
+    x, ldx = N.row_major(x)
+    R, fo = g.shape
+    fi = x.shape[1]
+    if out is None:
+        out = torch.empty((fo, fi), dtype=torch.float32, device=g.device)
+    nb = L.hl_wgrad_workspace(R, fo, fi)
+    ws = torch.empty(nb, dtype=torch.uint8, device=g.device)
+    N.check(L.hl_wgrad(g.data_ptr(), ldg, x.data_ptr(), ldx, R, fo, fi, out.data_ptr(), out.stride(0), 0,
+                       ws.data_ptr(), nb, N.stream_ptr()), "hl_wgrad")
+    return out
+
+
+def colsum(g):
+    L = N.lib()
+    g, ldg = N.row_major(g)
+    R, f = g.shape
+    out = torch.empty(f, dtype=torch.float32, device=g.device)
+    nb = L.hl_colsum_workspace(R, f)
+    ws = torch.empty(nb, dtype=torch.uint8, device=g.device)
+    N.check(L.hl_colsum(g.data_ptr(), ldg, R, f, out.data_ptr(), 0, ws.data_ptr(), nb, N.stream_ptr()), "hl_colsum")
+    return out
+
+
+class _Linear(torch.autograd.Function):
+    """y = [xa | xb] W^T + b without materialising the concat (xb optional); dgrad on cuBLAS, weight and
+    bias gradients through hl_wgrad / hl_colsum."""
+
+    @staticmethod
+    def forward(ctx, xa, xb, weight, bias):
+        N.require_cuda_f32(xa, xb, weight, bias)
+        d = xa.shape[1]
+        if xb is None:
+            y = torch.addmm(bias, xa, weight.t()) if bias is not None else torch.mm(xa, weight.t())
+        else:
+            y = torch.addmm(bias, xa, weight[:, :d].t()) if bias is not None else torch.mm(xa, weight[:, :d].t())
+            y.addmm_(xb, weight[:, d:].t())
+        ctx.save_for_backward(xa, xb, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        xa, xb, weight = ctx.saved_tensors
+        g = g.contiguous()
+        d = xa.shape[1]
+        ga = gb = gw = gbias = None
+        if ctx.needs_input_grad[0]:
+            ga = torch.mm(g, weight[:, :d])
+        if xb is not None and ctx.needs_input_grad[1]:
+            gb = torch.mm(g, weight[:, d:])
+        if ctx.needs_input_grad[2]:
+            gw = torch.empty_like(weight)
+            wgrad(g, xa, gw[:, :d])
+            if xb is not None:
+                wgrad(g, xb, gw[:, d:])
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            gbias = colsum(g)
+        return ga, gb, gw, gbias
+
+
+def linear(x, weight, bias=None, x2=None):
+    return _Linear.apply(x, x2, weight, bias)
+
+
 class _PolyConv(torch.autograd.Function):
     """out = sum_k T_k(x) W_k^T + b for one operator (lib/Hodge_Cheb_Conv.py:480-515 / :394-439).
     x is [R, width] (already flattened), inner = last-dim size the Linear layers act on."""
@@ -87,10 +155,10 @@ class _PolyConv(torch.autograd.Function):
         for k in range(K):
             if ctx.needs_input_grad[5 + k]:
                 src = x if k == 0 else t[k - 1]
-                gws.append(torch.mm(g.t(), src.view(-1, inner)))
+                gws.append(wgrad(g, src.view(-1, inner)))
             else:
                 gws.append(None)
-        gb = g.sum(0) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
+        gb = colsum(g) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
         return (gx, gb, None, None, None, *gws)
 
 

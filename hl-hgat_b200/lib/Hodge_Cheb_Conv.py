@@ -263,11 +263,9 @@ def _mlp(seq, transferred, own, nvalid=None):
     """Linear(cat[transferred, own]) -> BN -> ReLU -> Linear -> BN -> ReLU without materialising the
     concat: the first Linear is split over its two column blocks (lib/Hodge_Cheb_Conv.py:307-308)."""
     lin0, bn0, _, lin1, bn1, _ = seq
-    d = transferred.shape[1]
-    h = torch.addmm(lin0.bias, transferred, lin0.weight[:, :d].t())
-    h = h.addmm(own, lin0.weight[:, d:].t())
+    h = F_hl.linear(transferred, lin0.weight, lin0.bias, x2=own)
     h = _bn_relu(bn0, h, 0.0, nvalid)
-    h = torch.addmm(lin1.bias, h, lin1.weight.t())
+    h = F_hl.linear(h, lin1.weight, lin1.bias)
     return _bn_relu(bn1, h, 0.0, nvalid)
 
 

@@ -214,6 +214,20 @@ int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64_t ld_y,
                   void* workspace, size_t workspace_bytes, hl_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Weight and bias gradients of the dense layers as deterministic split-row reductions.
+ *   hl_wgrad : dw[fo,fi] (=|+=) g[R,fo]^T x[R,fi]        hl_colsum : out[f] (=|+=) sum_r g[r,f]
+ * Replaces: autograd of `lins[k](T_k)` / nn.Linear (`lib/Hodge_Cheb_Conv.py:487,497,509`, `:277-288`):
+ * cuBLAS walks all R rows with one CTA per 64x64 output tile; here rows are split over CTAs, partial
+ * tiles are summed in a fixed order (no atomics).  fp32 FMA.
+ * -------------------------------------------------------------------------------------------- */
+size_t hl_wgrad_workspace(int32_t nrows, int32_t fo, int32_t fi);
+int hl_wgrad(const float* g, int64_t ld_g, const float* x, int64_t ld_x, int32_t nrows, int32_t fo, int32_t fi,
+             float* dw, int64_t ld_dw, int accumulate, void* workspace, size_t workspace_bytes, hl_stream_t stream);
+size_t hl_colsum_workspace(int32_t nrows, int32_t width);
+int hl_colsum(const float* g, int64_t ld_g, int32_t nrows, int32_t width, float* out, int accumulate,
+              void* workspace, size_t workspace_bytes, hl_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
  * Simplex-graph construction for a whole mini-batch (block-diagonal), on the GPU.
  * Replaces: Dataset.process lib/Hodge_Dataset.py:447-456,467-468 (to_undirected -> i<j ->
  * dense B1 -> B1 B1^T -> eigh -> 2L/lambda_max -> dense_to_sparse), the same tail of MLGC

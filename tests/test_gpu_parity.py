@@ -330,3 +330,17 @@ def test_determinism_two_runs_bit_identical():
         p.abs().mean().backward()
         outs.append((p.detach().clone(), model.NEConv00.module_0.lins[1].weight.grad.clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("R,fo,fi", [(24000, 64, 64), (5000, 256, 704), (333, 5, 7), (1, 64, 28), (4097, 128, 10)])
+def test_wgrad_and_colsum_vs_torch(R, fo, fi):
+    torch.manual_seed(0)
+    g, x = torch.randn(R, fo, device=DEV), torch.randn(R, fi + 8, device=DEV)[:, 4:4 + fi]
+    ref = (g.double().t() @ x.double()).float()
+    got = F_hl.wgrad(g, x)
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-3 * max(1.0, R ** 0.5 / 30)), (got - ref).abs().max()
+    wide = torch.zeros(fo, 2 * fi, device=DEV)
+    F_hl.wgrad(g, x, wide[:, fi:])
+    assert torch.equal(wide[:, fi:], got) and float(wide[:, :fi].abs().max()) == 0.0
+    assert torch.equal(F_hl.wgrad(g, x), got)                                   # deterministic
+    close(F_hl.colsum(g), g.double().sum(0).float(), atol=1e-3)
