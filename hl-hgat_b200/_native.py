@@ -23,13 +23,13 @@ _vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_si
 
 
 class SpmmProblem(C.Structure):
-    _fields_ = [("rowptr", _vp), ("colidx", _vp), ("vals", _vp), ("nrows", _i32), ("reserved", _i32),
+    _fields_ = [("rowptr", _vp), ("colidx", _vp), ("vals", _vp), ("nrows", _i32), ("nnz_hint", _i32),
                 ("xg", _vp), ("ld_xg", _i64), ("p1", _vp), ("ld_p1", _i64), ("p2", _vp), ("ld_p2", _i64),
                 ("p3", _vp), ("ld_p3", _i64), ("out", _vp), ("ld_out", _i64)]
 
 
 class ConvSide(C.Structure):
-    _fields_ = [("rowptr", _vp), ("colidx", _vp), ("vals", _vp), ("nrows", _i32), ("reserved", _i32),
+    _fields_ = [("rowptr", _vp), ("colidx", _vp), ("vals", _vp), ("nrows", _i32), ("nnz_hint", _i32),
                 ("x", _vp), ("ld_x", _i64), ("t", _vp), ("ld_t", _i64), ("t_stride", _i64), ("g0", _vp), ("ld_g0", _i64)]
 
 

@@ -8,6 +8,9 @@
 // (Laguerre / Chebyshev step or a general linear combination for the adjoint) is applied in registers
 // before the single store, so T_{k+1} never makes an extra round trip through HBM.  Up to four
 // operators (node-side L0 and edge-side L1 of a block) share one launch.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace hl {
@@ -145,6 +148,19 @@ static void launch_epi(dim3 grid, cudaStream_t stream, const SpmmBatch& b, int32
   }
 }
 
+int launch_poly_spmm_staged(const hl_spmm_problem* probs, int n, int32_t width, int epi, float c0, float c1, float c2,
+                            float c3, cudaStream_t stream);   // poly_spmm_staged.cu
+
+// HL_SPMM_MODE = auto (default) | rows (per-row kernel only) | staged (staged kernel whenever it applies)
+static int spmm_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("HL_SPMM_MODE");
+    mode = (e && !strcmp(e, "rows")) ? 1 : 0;
+  }
+  return mode;
+}
+
 static int launch_poly_spmm(const hl_spmm_problem* probs, int n, int32_t width, int epi, const float* c,
                             cudaStream_t stream) {
   if (!probs || n < 1 || n > HL_MAX_SPMM_PROBLEMS || width < 1) return HL_ERR_INVALID;
@@ -160,6 +176,12 @@ static int launch_poly_spmm(const hl_spmm_problem* probs, int n, int32_t width, 
     V = min(V, vec_for(P.p1, P.ld_p1, width, V));
     V = min(V, vec_for(P.p2, P.ld_p2, width, V));
     V = min(V, vec_for(P.p3, P.ld_p3, width, V));
+  }
+  if (V == 4 && spmm_mode() == 0) {
+    float s0 = c ? c[0] : 0.f, s1 = c ? c[1] : 0.f, s2 = c ? c[2] : 0.f, s3 = c ? c[3] : 0.f;
+    if (epi == HL_EPI_LAGUERRE_STEP) { const float k = s0; s0 = k; s1 = 2.f * k + 1.f; s2 = k + 1.f; }
+    const int rc = launch_poly_spmm_staged(probs, n, width, epi, s0, s1, s2, s3, stream);
+    if (rc != 1) return rc;                                  // 1 = not applicable, fall through
   }
   // two vectors per lane whenever the row is wide enough to keep >= 4 lanes busy: halves the
   // per-row index/address instruction overhead and every lane still reads full 128-byte lines
@@ -227,7 +249,7 @@ extern "C" int hl_poly_basis_fwd(int family, int K, const hl_conv_side* sides, i
       auto T = [&](int j) -> const float* { return j == 0 ? S.x : S.t + (int64_t)(j - 1) * S.t_stride; };
       auto LD = [&](int j) -> int64_t { return j == 0 ? S.ld_x : S.ld_t; };
       hl_spmm_problem& P = pr[s];
-      P.rowptr = S.rowptr; P.colidx = S.colidx; P.vals = S.vals; P.nrows = S.nrows; P.reserved = 0;
+      P.rowptr = S.rowptr; P.colidx = S.colidx; P.vals = S.vals; P.nrows = S.nrows; P.nnz_hint = S.nnz_hint;
       P.xg = T(k); P.ld_xg = LD(k);
       P.p1 = T(k); P.ld_p1 = LD(k);
       P.p2 = k > 0 ? T(k - 1) : nullptr; P.ld_p2 = k > 0 ? LD(k - 1) : 0;
@@ -261,7 +283,7 @@ extern "C" int hl_poly_basis_bwd(int family, int K, const hl_conv_side* sides, i
       auto Gp = [&](int j) -> float* { return j == 0 ? S.g0 : S.t + (int64_t)(j - 1) * S.t_stride; };
       auto LD = [&](int j) -> int64_t { return j == 0 ? S.ld_g0 : S.ld_t; };
       hl_spmm_problem& P = pr[s];
-      P.rowptr = S.rowptr; P.colidx = S.colidx; P.vals = S.vals; P.nrows = S.nrows; P.reserved = 0;
+      P.rowptr = S.rowptr; P.colidx = S.colidx; P.vals = S.vals; P.nrows = S.nrows; P.nnz_hint = S.nnz_hint;
       P.xg = Gp(k + 1); P.ld_xg = LD(k + 1);
       P.p1 = (bk != 0.f) ? Gp(k + 1) : nullptr; P.ld_p1 = LD(k + 1);
       P.p2 = (k + 2 <= K - 1 && ck1 != 0.f) ? Gp(k + 2) : nullptr; P.ld_p2 = (k + 2 <= K - 1) ? LD(k + 2) : 0;

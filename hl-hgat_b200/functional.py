@@ -18,6 +18,7 @@ def _side(csr, nrows, x=None, ld_x=0, t=None, ld_t=0, t_stride=0, g0=None, ld_g0
     s = N.ConvSide()
     s.rowptr, s.colidx, s.vals = csr[0].data_ptr(), csr[1].data_ptr(), csr[2].data_ptr()
     s.nrows = nrows
+    s.nnz_hint = min(int(csr[1].numel()), 2 ** 31 - 1)
     s.x, s.ld_x = N.ptr(x), ld_x
     s.t, s.ld_t, s.t_stride = N.ptr(t), ld_t, t_stride
     s.g0, s.ld_g0 = N.ptr(g0), ld_g0
@@ -181,6 +182,7 @@ def poly_spmm(csr, nrows, xg, epi, c=(0.0, 0.0, 0.0, 0.0), p1=None, p2=None, p3=
         out = torch.empty((nrows, width), dtype=torch.float32, device=xg.device)
     P = (N.SpmmProblem * 1)()
     P[0].rowptr, P[0].colidx, P[0].vals, P[0].nrows = csr[0].data_ptr(), csr[1].data_ptr(), csr[2].data_ptr(), nrows
+    P[0].nnz_hint = min(int(csr[1].numel()), 2 ** 31 - 1)
     P[0].xg, P[0].ld_xg = xg.data_ptr(), ldx
     for name, t in (("p1", p1), ("p2", p2), ("p3", p3)):
         if t is not None:

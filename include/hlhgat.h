@@ -90,7 +90,7 @@ typedef struct {
   const int32_t* colidx;
   const float* vals;
   int32_t nrows;
-  int32_t reserved;
+  int32_t nnz_hint;                /* total nnz if known on the host (0 = unknown): selects the staged kernel */
   const float* xg;  int64_t ld_xg;
   const float* p1;  int64_t ld_p1;
   const float* p2;  int64_t ld_p2;
@@ -126,7 +126,7 @@ typedef struct {
   const int32_t* colidx;
   const float* vals;
   int32_t nrows;
-  int32_t reserved;
+  int32_t nnz_hint;        /* total nnz if known on the host, else 0 */
   const float* x;  int64_t ld_x;   /* forward: input x.   backward: unused (NULL) */
   float* t;        int64_t ld_t;   /* forward: basis out (K-1 blocks). backward: gt (in/out) */
   int64_t t_stride;                /* elements between consecutive blocks of t */
