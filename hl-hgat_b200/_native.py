@@ -41,6 +41,7 @@ _SIGNATURES = {
     "hl_launch_count": (C.c_ulonglong, []),
     "hl_csr_from_coo_workspace": (_sz, [_i64, _i64]),
     "hl_csr_from_coo": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, C.c_int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hl_set_spmm_mode": (None, [C.c_int]),
     "hl_poly_spmm": (C.c_int, [C.POINTER(SpmmProblem), C.c_int, _i32, C.c_int, C.POINTER(_f32), _vp]),
     "hl_poly_basis_fwd": (C.c_int, [C.c_int, C.c_int, C.POINTER(ConvSide), C.c_int, _i32, _vp]),
     "hl_poly_basis_bwd": (C.c_int, [C.c_int, C.c_int, C.POINTER(ConvSide), C.c_int, _i32, _vp]),
@@ -56,6 +57,10 @@ _SIGNATURES = {
     "hl_laplacian_rowptr_workspace": (_sz, [_i32, _i32]),
     "hl_laplacian_rowptr": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hl_laplacian_fill": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hl_tf32_split": (C.c_int, [_vp, _i64, _i32, _i32, C.c_int, _vp, _vp, _i64, _vp]),
+    "hl_gemm_tf32x3": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _i64, C.c_int, _vp]),
+    "hl_wgrad_tf32x3_workspace": (_sz, [_i32, _i32, _i32]),
+    "hl_wgrad_tf32x3": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, C.c_int, _vp, _sz, _vp]),
     "hl_wgrad_workspace": (_sz, [_i32, _i32, _i32]),
     "hl_wgrad": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, C.c_int, _vp, _sz, _vp]),
     "hl_colsum_workspace": (_sz, [_i32, _i32]),

@@ -1,0 +1,475 @@
+// fp32-accurate GEMM on the 5th-generation tensor cores (tcgen05, kind::tf32) by 3xTF32 splitting:
+//     C[M,N] = A[M,K] * B[N,K]^T (+ bias | + C)        A, B row-major with K contiguous ("K-major")
+// Every fp32 operand x is split as x = hi + lo with hi = x & 0xffffe000 (exact in tf32) and lo = x - hi;
+// the product is accumulated as  A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  in an fp32 TMEM accumulator (the dropped
+// lo*lo term is ~2^-22 relative), which keeps the reference's fp32 parity bar (rtol 1e-4) that plain
+// 1xTF32 (2^-11) would break.  This is the dense Theta / MLP feature transform of the path
+// (lib/Hodge_Cheb_Conv.py:487,497,509 and :277-288).
+//
+// Structure (one CTA = one 128 x BN output tile, BN = N <= 256):
+//   warp 0      TMA producer: A tile (128x32 fp32, 128B swizzle) + pre-split B_hi / B_lo tiles per k-block
+//   warps 2-5   converters: split the landed A tile in place into hi (in place) and lo (second buffer) --
+//               an elementwise pass, so it is oblivious to the swizzled layout -- then
+//               fence.proxy.async and signal the MMA warp; after the main loop the same warps run the
+//               epilogue (tcgen05.ld 32x32b -> registers -> bias / accumulate -> 128-bit global stores)
+//   warp 1      one elected lane issues 3 x 4 tcgen05.mma (M=128, N=BN, K=8) per k-block into TMEM and
+//               releases the stage with tcgen05.commit
+// B (the weights, <= 256 x 1408) is split once per call by hl_tf32_split into global hi / lo copies.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace hl {
+
+constexpr int kGmBM = 128;
+constexpr int kGmBK = 32;                 // floats per k-block = one 128-byte swizzle span
+constexpr int kGmThreads = 192;
+constexpr int kGmConvThreads = 128;
+
+__device__ __forceinline__ uint32_t gm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void gm_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gm_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void gm_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gm_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void gm_mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gm_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gm_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "GW_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra GD_%=;\n\t"
+      "bra GW_%=;\n\t"
+      "GD_%=:\n\t}" ::"r"(gm_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void gm_tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          gm_smem_u32(dst)),
+      "l"(map), "r"(gm_smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void gm_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void gm_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(gm_smem_u32(bar)) : "memory");
+}
+
+// K-major, 128-byte swizzle: rows of 128 B, 8-row atoms of 1024 B (SBO), descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t gm_desc_kmajor_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                       // version
+  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
+
+// MN-major tf32 operands have exactly one legal shared-memory layout on sm_100: SWIZZLE_128B_BASE32B
+// (32-byte chunks swizzled inside the 128-byte row, 4-row / 512-byte atoms; TMA mode
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  32 MN elements (128 B) per k-row; 4-row k-groups every 512 B (SBO);
+// 32-element MN blocks every `mn_block_bytes` (LBO) -- what {32 cols, 32 rows} TMA boxes of a row-major
+// [K rows, MN cols] array produce when stacked one after another.
+__device__ __forceinline__ uint64_t gm_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t mn_block_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((mn_block_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                       // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+struct GemmParams {
+  int32_t M, N, K, bn, stages, tmem_cols;
+  const float* bias;
+  float* C;
+  int64_t ldc;
+  int32_t accumulate;
+  int32_t k_per_split;      // wgrad mode: rows of the contraction handled by one blockIdx.z (multiple of 32)
+  int64_t split_stride;     // wgrad mode: elements between partial outputs of consecutive splits
+};
+
+// MODE 0: C = A[M,K] B[N,K]^T, both K-major, B pre-split (map_b = hi, map_b2 = lo).
+// MODE 1: weight gradient C[M,N] = G[R,M]^T X[R,N] over the row range of blockIdx.z: both operands MN-major
+//         (contraction over the rows), both split in the kernel; map_a = G, map_b = X, map_b2 unused.
+template <int MODE>
+__global__ void __launch_bounds__(kGmThreads, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+                   const __grid_constant__ CUtensorMap map_blo, const GemmParams P) {
+  extern __shared__ __align__(1024) unsigned char gm_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bn = P.bn, stages = P.stages;
+  const uint32_t a_bytes = kGmBM * kGmBK * 4, b_bytes = (uint32_t)bn * kGmBK * 4;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  unsigned char* base = gm_smem;                                   // 1024-byte aligned by the launch
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)stages * stage_bytes);
+  uint64_t* full_bar = bars;                 // [stages]  TMA bytes landed
+  uint64_t* conv_bar = bars + stages;        // [stages]  A split done
+  uint64_t* empty_bar = bars + 2 * stages;   // [stages]  MMAs of the stage retired
+  uint64_t* acc_bar = bars + 3 * stages;     // [1]       accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + 1);
+
+  const int m0 = blockIdx.x * kGmBM;
+  const int n0 = blockIdx.y * bn;
+  const int k_begin = MODE == 1 ? (int)blockIdx.z * P.k_per_split : 0;
+  const int k_end = MODE == 1 ? min(P.K, k_begin + P.k_per_split) : P.K;
+  const int num_kb = k_end > k_begin ? (k_end - k_begin + kGmBK - 1) / kGmBK : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      gm_mbar_init(&full_bar[s], 1);
+      gm_mbar_init(&conv_bar[s], kGmConvThreads);
+      gm_mbar_init(&empty_bar[s], 1);
+    }
+    gm_mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {                                                  // TMEM allocation (whole warp)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gm_smem_u32(tmem_slot)),
+                 "r"((uint32_t)P.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------ TMA producer ------------------------------------
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t round = (uint32_t)(kb / stages);
+        gm_mbar_wait(&empty_bar[s], (round & 1u) ^ 1u);
+        unsigned char* st = base + (size_t)s * stage_bytes;
+        if (MODE == 0) {
+          gm_mbar_arrive_expect_tx(&full_bar[s], a_bytes + 2 * b_bytes);
+          gm_tma_load_2d(st, &map_a, &full_bar[s], kb * kGmBK, m0);
+          gm_tma_load_2d(st + 2 * a_bytes, &map_bhi, &full_bar[s], kb * kGmBK, n0);
+          gm_tma_load_2d(st + 2 * a_bytes + b_bytes, &map_blo, &full_bar[s], kb * kGmBK, n0);
+        } else {
+          // stack of {32 cols, 32 rows} boxes: 4 for the 128 output rows (G columns), bn/32 for the output columns
+          gm_mbar_arrive_expect_tx(&full_bar[s], a_bytes + b_bytes);
+          const int row = k_begin + kb * kGmBK;
+          for (int j = 0; j < kGmBM / 32; ++j) gm_tma_load_2d(st + j * 4096, &map_a, &full_bar[s], m0 + 32 * j, row);
+          for (int j = 0; j < bn / 32; ++j)
+            gm_tma_load_2d(st + 2 * a_bytes + j * 4096, &map_bhi, &full_bar[s], n0 + 32 * j, row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------ MMA issuer ------------------------------------
+    if (lane == 0) {
+      // instruction descriptor: D=F32, A=B=TF32, K-major both, N = bn, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kGmBM >> 4) << 24) |
+                             (MODE == 1 ? ((1u << 15) | (1u << 16)) : 0u);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t round = (uint32_t)(kb / stages);
+        gm_mbar_wait(&conv_bar[s], round & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = gm_smem_u32(base + (size_t)s * stage_bytes);
+        const uint32_t a_hi = st, a_lo = st + a_bytes, b_hi = st + 2 * a_bytes, b_lo = st + 2 * a_bytes + b_bytes;
+#pragma unroll
+        for (int k = 0; k < kGmBK / 8; ++k) {
+          uint64_t dah, dal, dbh, dbl;
+          if (MODE == 0) {
+            const uint32_t off = (uint32_t)k * 32u;                 // 8 tf32 = 32 bytes along K inside the swizzle span
+            dah = gm_desc_kmajor_sw128(a_hi + off); dal = gm_desc_kmajor_sw128(a_lo + off);
+            dbh = gm_desc_kmajor_sw128(b_hi + off); dbl = gm_desc_kmajor_sw128(b_lo + off);
+          } else {
+            const uint32_t off = (uint32_t)k * 1024u;               // 8 k-rows = one 1 KB atom group
+            dah = gm_desc_mnmajor_sw128(a_hi + off, 4096); dal = gm_desc_mnmajor_sw128(a_lo + off, 4096);
+            dbh = gm_desc_mnmajor_sw128(b_hi + off, 4096); dbl = gm_desc_mnmajor_sw128(b_lo + off, 4096);
+          }
+          gm_mma_tf32(tmem_base, dal, dbh, idesc, (kb | k) ? 1u : 0u);   // small terms first
+          gm_mma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          gm_mma_tf32(tmem_base, dah, dbh, idesc, 1u);
+        }
+        gm_commit(&empty_bar[s]);                                   // frees the stage when these MMAs retire
+      }
+      gm_commit(acc_bar);
+    }
+  } else {
+    // ------------------------------------ converters, then epilogue ------------------------------------
+    const int ct = threadIdx.x - 64;                                // 0..127
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % stages;
+      const uint32_t round = (uint32_t)(kb / stages);
+      gm_mbar_wait(&full_bar[s], round & 1u);
+      float4* a = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes);
+      float4* alo = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + a_bytes);
+#pragma unroll
+      for (int i = 0; i < (kGmBM * kGmBK / 4) / kGmConvThreads; ++i) {
+        const int idx = ct + i * kGmConvThreads;
+        const float4 x = a[idx];
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+        h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+        h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+        h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+        l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+        a[idx] = h;
+        alo[idx] = l;
+      }
+      if (MODE == 1) {
+        float4* b = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + 2 * a_bytes);
+        float4* blo = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + 2 * a_bytes + b_bytes);
+        for (int idx = ct; idx < (int)(b_bytes / 16); idx += kGmConvThreads) {
+          const float4 x = b[idx];
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+          l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+          b[idx] = h;
+          blo[idx] = l;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
+      gm_mbar_arrive(&conv_bar[s]);
+    }
+    // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (= output rows)
+    gm_mbar_wait(acc_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* Cbase = P.C + (MODE == 1 ? (int64_t)blockIdx.z * P.split_stride : 0);
+    const int quad = warp & 3;
+    const int row = m0 + quad * 32 + lane;
+    const bool vec_ok = (P.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
+    for (int c = 0; c < bn; c += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < P.M) {
+        float* crow = Cbase + (int64_t)row * P.ldc + n0 + c;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int col = n0 + c + j;
+          if (col >= P.N || c + j >= bn) break;                   // tile overhang / columns past this CTA's bn
+          float v[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) v[t] = num_kb > 0 ? __uint_as_float(r[j + t]) : 0.f;
+          if (P.bias) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (col + t < P.N) v[t] += __ldg(P.bias + col + t);
+          }
+          if (vec_ok && col + 3 < P.N) {
+            float4* dst = reinterpret_cast<float4*>(crow + j);
+            if (P.accumulate) {
+              const float4 o = *dst;
+              v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+            }
+            *dst = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (col + t < P.N) crow[j + t] = P.accumulate ? crow[j + t] + v[t] : v[t];
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
+  }
+}
+
+// x -> hi (low 13 mantissa bits cleared) and lo = x - hi; optional transpose: out[c, r] = split(src[r, c])
+__global__ void tf32_split_kernel(const float* __restrict__ src, int64_t ld_src, int32_t rows, int32_t cols, int transpose,
+                                  float* __restrict__ hi, float* __restrict__ lo, int64_t ld_out) {
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+    const float x = src[(int64_t)r * ld_src + c];
+    const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    const int64_t o = transpose ? (int64_t)c * ld_out + r : (int64_t)r * ld_out + c;
+    hi[o] = h;
+    lo[o] = x - h;
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] with row pitch ld (elements); box = {32 cols, box_rows}; 128-byte swizzle
+static bool make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                     int box_cols = kGmBK, bool mn_major = false) {
+  auto fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace hl
+
+extern "C" int hl_tf32_split(const float* src, int64_t ld_src, int32_t rows, int32_t cols, int transpose,
+                             float* hi, float* lo, int64_t ld_out, hl_stream_t stream) {
+  using namespace hl;
+  if (rows < 0 || cols < 0 || !hi || !lo) return HL_ERR_INVALID;
+  if (rows == 0 || cols == 0) return HL_OK;
+  if (!src) return HL_ERR_INVALID;
+  const int64_t n = (int64_t)rows * cols;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  tf32_split_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(src, ld_src, rows, cols, transpose, hi, lo, ld_out);
+  HL_LAUNCH_CHECK("tf32_split_kernel");
+  return HL_OK;
+}
+
+// returns HL_OK, or 1 when the shape / alignment is not supported (caller uses a library GEMM instead)
+extern "C" int hl_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb,
+                              int32_t M, int32_t N, int32_t K, const float* bias, float* C, int64_t ldc,
+                              int accumulate, hl_stream_t stream) {
+  using namespace hl;
+  if (M < 0 || N < 1 || K < 1 || !C) return HL_ERR_INVALID;
+  if (M == 0) return HL_OK;
+  if (!A || !Bhi || !Blo) return HL_ERR_INVALID;
+  // TMA: 16-byte aligned base and row pitch; MMA: N multiple of 16, one N tile of <= 256 columns per CTA
+  if (lda % 4 != 0 || ldb % 4 != 0 || !aligned_to(A, 16) || !aligned_to(Bhi, 16) || !aligned_to(Blo, 16)) return 1;
+  if (N % 16 != 0) return 1;
+  const int ntiles = (N + 255) / 256;
+  const int bn = ((N + ntiles - 1) / ntiles + 15) / 16 * 16;      // <= 256, multiple of 16; TMA zero-fills the overhang
+  int tmem_cols = 32;
+  while (tmem_cols < bn) tmem_cols <<= 1;
+  const size_t stage_bytes = 2 * (size_t)kGmBM * kGmBK * 4 + 2 * (size_t)bn * kGmBK * 4;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 4) stages = 4;
+  if (stages < 2) return 1;
+  const size_t smem = stages * stage_bytes + (3 * stages + 2) * sizeof(uint64_t) + 1024;
+
+  CUtensorMap ma, mbh, mbl;
+  if (!make_map(&ma, A, M, K, lda, kGmBM) || !make_map(&mbh, Bhi, N, K, ldb, bn) || !make_map(&mbl, Blo, N, K, ldb, bn))
+    return 1;
+  static bool configured = false;
+  if (!configured) {
+    HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  GemmParams P;
+  P.M = M; P.N = N; P.K = K; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
+  P.bias = bias; P.C = C; P.ldc = ldc; P.accumulate = accumulate; P.k_per_split = 0; P.split_stride = 0;
+  dim3 grid((M + kGmBM - 1) / kGmBM, ntiles);
+  gemm_tf32x3_kernel<0><<<grid, kGmThreads, smem, as_stream(stream)>>>(ma, mbh, mbl, P);
+  HL_LAUNCH_CHECK("gemm_tf32x3_kernel");
+  return HL_OK;
+}
+
+__global__ void gm_split_reduce_kernel(const float* __restrict__ partial, int32_t splits, int64_t split_stride, int32_t fo,
+                                       int32_t fi, float* __restrict__ dw, int64_t ld_dw, int accumulate) {
+  const int64_t n = (int64_t)fo * fi;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[(int64_t)k * split_stride + i];
+    const int64_t o = i / fi, c = i - o * fi;
+    float* p = dw + o * ld_dw + c;
+    *p = accumulate ? *p + s : s;
+  }
+}
+
+static int wgrad_tc_splits(int32_t nrows, int tiles) {
+  int s = (2 * 148 + tiles - 1) / tiles;
+  const int max_s = (nrows + 255) / 256;
+  if (s > max_s) s = max_s;
+  return s < 1 ? 1 : s;
+}
+
+extern "C" size_t hl_wgrad_tf32x3_workspace(int32_t nrows, int32_t fo, int32_t fi) {
+  if (nrows < 0 || fo < 1 || fi < 1) return 0;
+  const int ntiles = (fi + 255) / 256;
+  const int tiles = ((fo + hl::kGmBM - 1) / hl::kGmBM) * ntiles;
+  return (size_t)wgrad_tc_splits(nrows, tiles) * (size_t)fo * (size_t)fi * sizeof(float) + 256;
+}
+
+// dW[fo,fi] (=|+=) g[R,fo]^T x[R,fi] on the tensor cores (3xTF32), split over row ranges, partial tiles summed
+// in a fixed order.  Returns 1 when the shape is unsupported (caller falls back to hl_wgrad).
+extern "C" int hl_wgrad_tf32x3(const float* g, int64_t ld_g, const float* x, int64_t ld_x, int32_t nrows, int32_t fo,
+                               int32_t fi, float* dw, int64_t ld_dw, int accumulate, void* workspace,
+                               size_t workspace_bytes, hl_stream_t stream) {
+  using namespace hl;
+  if (nrows < 0 || fo < 1 || fi < 1 || !dw) return HL_ERR_INVALID;
+  if (nrows > 0 && (!g || !x)) return HL_ERR_INVALID;
+  if (ld_g % 4 != 0 || ld_x % 4 != 0 || !aligned_to(g, 16) || !aligned_to(x, 16)) return 1;
+  if (fo % 4 != 0 || fi % 32 != 0 || nrows < 512) return 1;
+  if (!workspace || workspace_bytes < hl_wgrad_tf32x3_workspace(nrows, fo, fi)) return HL_ERR_WORKSPACE;
+  const int ntiles = (fi + 255) / 256;
+  const int bn = ((fi + ntiles - 1) / ntiles + 31) / 32 * 32;     // multiple of 32: whole {32 x 32} boxes
+  int tmem_cols = 32;
+  while (tmem_cols < bn) tmem_cols <<= 1;
+  const size_t stage_bytes = 2 * (size_t)kGmBM * kGmBK * 4 + 2 * (size_t)bn * kGmBK * 4;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 4) stages = 4;
+  if (stages < 2) return 1;
+  const size_t smem = stages * stage_bytes + (3 * stages + 2) * sizeof(uint64_t) + 1024;
+  const int mtiles = (fo + kGmBM - 1) / kGmBM;
+  const int splits = wgrad_tc_splits(nrows, mtiles * ntiles);
+  const int k_per_split = ((nrows + splits - 1) / splits + 31) / 32 * 32;
+
+  CUtensorMap mg, mx;
+  if (!make_map(&mg, g, nrows, fo, ld_g, 32, 32, true) || !make_map(&mx, x, nrows, fi, ld_x, 32, 32, true)) return 1;
+  static bool configured = false;
+  if (!configured) {
+    HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  GemmParams P;
+  P.M = fo; P.N = fi; P.K = nrows; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
+  P.bias = nullptr; P.C = reinterpret_cast<float*>(workspace); P.ldc = fi; P.accumulate = 0;
+  P.k_per_split = k_per_split; P.split_stride = (int64_t)fo * fi;
+  dim3 grid(mtiles, ntiles, splits);
+  gemm_tf32x3_kernel<1><<<grid, kGmThreads, smem, as_stream(stream)>>>(mg, mx, mx, P);
+  HL_LAUNCH_CHECK("gemm_tf32x3_kernel<wgrad>");
+  const int64_t n = (int64_t)fo * fi;
+  gm_split_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, as_stream(stream)>>>(P.C, splits, P.split_stride, fo, fi, dw, ld_dw,
+                                                                               accumulate);
+  HL_LAUNCH_CHECK("gm_split_reduce_kernel");
+  return HL_OK;
+}

@@ -152,13 +152,13 @@ int launch_poly_spmm_staged(const hl_spmm_problem* probs, int n, int32_t width, 
                             float c3, cudaStream_t stream);   // poly_spmm_staged.cu
 
 // HL_SPMM_MODE = auto (default) | rows (per-row kernel only) | staged (staged kernel whenever it applies)
+static int g_spmm_mode = -1;
 static int spmm_mode() {
-  static int mode = -1;
-  if (mode < 0) {
+  if (g_spmm_mode < 0) {
     const char* e = getenv("HL_SPMM_MODE");
-    mode = (e && !strcmp(e, "rows")) ? 1 : 0;
+    g_spmm_mode = (e && !strcmp(e, "rows")) ? 1 : 0;
   }
-  return mode;
+  return g_spmm_mode;
 }
 
 static int launch_poly_spmm(const hl_spmm_problem* probs, int n, int32_t width, int epi, const float* c,
@@ -230,6 +230,8 @@ static void recurrence(int family, int k, float* a, float* b, float* c) {
 }
 
 }  // namespace hl
+
+extern "C" void hl_set_spmm_mode(int mode) { hl::g_spmm_mode = mode ? 1 : 0; }
 
 extern "C" int hl_poly_spmm(const hl_spmm_problem* problems, int nproblems, int32_t width, int epilogue,
                             const float* c, hl_stream_t stream) {

@@ -49,6 +49,50 @@ def poly_basis_bwd(family, K, ops, g0s, gts, width):
         N.check(L.hl_poly_basis_bwd(family, K, sides, len(ops), width, N.stream_ptr()), "hl_poly_basis_bwd")
 
 
+_GEMM_MODE = {"tensor": True}
+
+
+def set_dense_backend(name):
+    """"tcgen05" (default): 3xTF32 tensor-core GEMM from libhlhgat; "cublas": torch.mm (fp32 SIMT SGEMM)."""
+    _GEMM_MODE["tensor"] = name == "tcgen05"
+
+
+def dense(a, w, bias=None, out=None, accumulate=False, transpose_w=False):
+    """out (=|+=) a @ w.T (+ bias)   [transpose_w: a @ w].  fp32-accurate tcgen05 GEMM (3xTF32 split) when the
+    shape allows (N % 16 == 0, 16-byte aligned rows), else the cuBLAS fp32 GEMM."""
+    L = N.lib()
+    M, K = a.shape
+    n_out = w.shape[1] if transpose_w else w.shape[0]
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.float32, device=a.device)
+        accumulate = False
+    if _GEMM_MODE["tensor"] and M > 0 and n_out % 16 == 0 and a.stride(1) == 1 and a.stride(0) % 4 == 0 \
+            and a.data_ptr() % 16 == 0 and K % 4 == 0 and out.stride(1) == 1:
+        kp = K
+        hi = torch.empty((n_out, kp), dtype=torch.float32, device=a.device)
+        lo = torch.empty((n_out, kp), dtype=torch.float32, device=a.device)
+        # w is [n_out, K] (or [K, n_out] when transpose_w): split into tf32-exact hi and remainder lo, [n_out, K]
+        rows, cols = (K, n_out) if transpose_w else (n_out, K)
+        N.check(L.hl_tf32_split(w.data_ptr(), w.stride(0), rows, cols, 1 if transpose_w else 0,
+                                hi.data_ptr(), lo.data_ptr(), kp, N.stream_ptr()), "hl_tf32_split")
+        rc = L.hl_gemm_tf32x3(a.data_ptr(), a.stride(0), hi.data_ptr(), lo.data_ptr(), kp, M, n_out, K, N.ptr(bias),
+                              out.data_ptr(), out.stride(0), 1 if accumulate else 0, N.stream_ptr())
+        if rc == 0:
+            return out
+        if rc != 1:
+            N.check(rc, "hl_gemm_tf32x3")
+    wt = w if transpose_w else w.t()
+    if accumulate:
+        out.addmm_(a, wt)
+        if bias is not None:
+            out.add_(bias)
+    elif bias is not None:
+        torch.addmm(bias, a, wt, out=out)
+    else:
+        torch.mm(a, wt, out=out)
+    return out
+
+
 def wgrad(g, x, out=None):
     """dW[Fo,Fi] = g[R,Fo]^T x[R,Fi] (deterministic split-row reduction); `out` may be a column slice."""
     L = N.lib()
@@ -58,6 +102,15 @@ def wgrad(g, x, out=None):
     fi = x.shape[1]
     if out is None:
         out = torch.empty((fo, fi), dtype=torch.float32, device=g.device)
+    if _GEMM_MODE["tensor"]:
+        nb = L.hl_wgrad_tf32x3_workspace(R, fo, fi)
+        ws = torch.empty(nb, dtype=torch.uint8, device=g.device)
+        rc = L.hl_wgrad_tf32x3(g.data_ptr(), ldg, x.data_ptr(), ldx, R, fo, fi, out.data_ptr(), out.stride(0), 0,
+                               ws.data_ptr(), nb, N.stream_ptr())
+        if rc == 0:
+            return out
+        if rc != 1:
+            N.check(rc, "hl_wgrad_tf32x3")
     nb = L.hl_wgrad_workspace(R, fo, fi)
     ws = torch.empty(nb, dtype=torch.uint8, device=g.device)
     N.check(L.hl_wgrad(g.data_ptr(), ldg, x.data_ptr(), ldx, R, fo, fi, out.data_ptr(), out.stride(0), 0,
@@ -84,11 +137,13 @@ class _Linear(torch.autograd.Function):
     def forward(ctx, xa, xb, weight, bias):
         N.require_cuda_f32(xa, xb, weight, bias)
         d = xa.shape[1]
+        xa = xa.contiguous() if xa.stride(1) != 1 else xa
         if xb is None:
-            y = torch.addmm(bias, xa, weight.t()) if bias is not None else torch.mm(xa, weight.t())
+            y = dense(xa, weight, bias)
         else:
-            y = torch.addmm(bias, xa, weight[:, :d].t()) if bias is not None else torch.mm(xa, weight[:, :d].t())
-            y.addmm_(xb, weight[:, d:].t())
+            xb = xb.contiguous() if xb.stride(1) != 1 else xb
+            y = dense(xa, weight[:, :d], bias)
+            dense(xb, weight[:, d:], None, out=y, accumulate=True)
         ctx.save_for_backward(xa, xb, weight)
         ctx.has_bias = bias is not None
         return y
@@ -100,9 +155,9 @@ class _Linear(torch.autograd.Function):
         d = xa.shape[1]
         ga = gb = gw = gbias = None
         if ctx.needs_input_grad[0]:
-            ga = torch.mm(g, weight[:, :d])
+            ga = dense(g, weight[:, :d], transpose_w=True)
         if xb is not None and ctx.needs_input_grad[1]:
-            gb = torch.mm(g, weight[:, d:])
+            gb = dense(g, weight[:, d:], transpose_w=True)
         if ctx.needs_input_grad[2]:
             gw = torch.empty_like(weight)
             wgrad(g, xa, gw[:, :d])
@@ -129,10 +184,9 @@ class _PolyConv(torch.autograd.Function):
         R, width = x.shape
         (t,) = poly_basis_fwd(family, K, [op], [x], width)
         xv = x.view(-1, inner)
-        w0 = weights[0]
-        out = torch.addmm(bias, xv, w0.t()) if bias is not None else torch.mm(xv, w0.t())
+        out = dense(xv, weights[0], bias)
         for k in range(1, K):
-            out.addmm_(t[k - 1].view(-1, inner), weights[k].t())
+            dense(t[k - 1].view(-1, inner), weights[k], None, out=out, accumulate=True)
         ctx.op, ctx.family, ctx.inner, ctx.has_bias = op, family, inner, bias is not None
         ctx.save_for_backward(x, t, *weights)
         return out
@@ -146,10 +200,10 @@ class _PolyConv(torch.autograd.Function):
         need_x = ctx.needs_input_grad[0]
         gx = None
         if need_x:
-            g0 = torch.mm(g, weights[0]).view(R, width)
+            g0 = dense(g, weights[0], transpose_w=True).view(R, width)
             gt = torch.empty((max(K - 1, 0), R, width), dtype=torch.float32, device=x.device)
             for k in range(1, K):
-                torch.mm(g, weights[k], out=gt[k - 1].view(-1, inner))
+                dense(g, weights[k], out=gt[k - 1].view(-1, inner), transpose_w=True)
             poly_basis_bwd(ctx.family, K, [op], [g0], [gt], width)
             gx = g0
         gws = []

@@ -106,6 +106,9 @@ enum {
   HL_EPI_LINCOMB = 4
 };
 #define HL_MAX_SPMM_PROBLEMS 4
+/* kernel selection: 0 = auto (row-window staged kernel whenever it applies), 1 = per-row kernel only.
+ * Also settable with the environment variable HL_SPMM_MODE=rows.  Both kernels give identical bits. */
+void hl_set_spmm_mode(int mode);
 int hl_poly_spmm(const hl_spmm_problem* problems /* host */, int nproblems, int32_t width, int epilogue,
                  const float* c /* host, 4 floats */, hl_stream_t stream);
 
@@ -212,6 +215,30 @@ int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64_t ld_y,
                   const float* gamma, const float* stats, float eps, float slope,
                   float* dx, int64_t ld_dx, float* dgamma, float* dbeta, const int32_t* nvalid,
                   void* workspace, size_t workspace_bytes, hl_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * fp32-accurate dense transform on the tcgen05 tensor cores (3xTF32 split, fp32 TMEM accumulator):
+ *   hl_gemm_tf32x3 : C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) , or C += ... when accumulate != 0
+ * A row-major [M,K] (pitch lda), B = the layer weight [N,K] pre-split by hl_tf32_split into
+ * hi (tf32-exact) and lo (remainder) copies [N,K] (pitch ldb).  Replaces the cuBLAS SGEMM behind
+ * `lins[k](T_k)` / nn.Linear (lib/Hodge_Cheb_Conv.py:487,497,509, :277-288) and its data gradient
+ * (B = W^T, hl_tf32_split(transpose=1)).  Requirements: lda, ldb multiples of 4, 16-byte aligned
+ * bases, N a multiple of 16 (one CTA covers 128 rows x min(N,256) columns).  Returns 1 (not an
+ * error) when the shape is unsupported so the caller can use a library GEMM.
+ * -------------------------------------------------------------------------------------------- */
+int hl_tf32_split(const float* src, int64_t ld_src, int32_t rows, int32_t cols, int transpose,
+                  float* hi, float* lo, int64_t ld_out, hl_stream_t stream);
+int hl_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb,
+                   int32_t M, int32_t N, int32_t K, const float* bias, float* C, int64_t ldc,
+                   int accumulate, hl_stream_t stream);
+/* Weight gradient on the same tensor-core path: dw[fo,fi] (=|+=) g[R,fo]^T x[R,fi].  Both operands are
+ * consumed MN-major straight from their row-major storage ({32 x 32} TMA boxes, no transposes), split into
+ * hi/lo inside the kernel, the R rows are divided over CTAs and the partial tiles are summed in a fixed
+ * order (deterministic).  Needs fo % 4 == 0, fi % 32 == 0, R >= 512; returns 1 otherwise (use hl_wgrad). */
+size_t hl_wgrad_tf32x3_workspace(int32_t nrows, int32_t fo, int32_t fi);
+int hl_wgrad_tf32x3(const float* g, int64_t ld_g, const float* x, int64_t ld_x, int32_t nrows, int32_t fo, int32_t fi,
+                    float* dw, int64_t ld_dw, int accumulate, void* workspace, size_t workspace_bytes,
+                    hl_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
  * Weight and bias gradients of the dense layers as deterministic split-row reductions.
