@@ -71,7 +71,8 @@ __device__ __forceinline__ void warp_sum2(double& a, double& b) {
 
 __global__ void bn_stats_final_kernel(const double* __restrict__ partial, int nblk, const float* __restrict__ x,
                                       int32_t nrows_cap, const int32_t* __restrict__ nvalid, int32_t width,
-                                      float* __restrict__ stats) {
+                                      float* __restrict__ stats, float* __restrict__ running_mean,
+                                      float* __restrict__ running_var, float momentum) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (c >= width) return;
@@ -85,8 +86,15 @@ __global__ void bn_stats_final_kernel(const double* __restrict__ partial, int nb
   if (lane == 0) {
     if (nrows > 0) {
       const double n = (double)nrows, m = a / n;
-      stats[c] = (float)((double)__ldg(x + c) + m);
-      stats[width + c] = (float)fmax(b / n - m * m, 0.0);
+      const float mean = (float)((double)__ldg(x + c) + m);
+      const float var = (float)fmax(b / n - m * m, 0.0);
+      stats[c] = mean;
+      stats[width + c] = var;
+      if (running_mean) {                                     // nn.BatchNorm1d bookkeeping: unbiased variance
+        const float unbias = (float)(n / fmax(n - 1.0, 1.0));
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * unbias;
+      }
     } else {
       stats[c] = 0.f;
       stats[width + c] = 0.f;
@@ -255,6 +263,7 @@ extern "C" size_t hl_bn_workspace(int32_t nrows, int32_t width) {
 extern "C" int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_t width,
                              const float* gamma, const float* beta, float eps, float slope,
                              float* y, int64_t ld_y, float* stats, const int32_t* nvalid,
+                             float* running_mean, float* running_var, float momentum,
                              void* workspace, size_t workspace_bytes, hl_stream_t stream) {
   using namespace hl;
   if (nrows < 1 || width < 1 || !x || !y || !stats) return HL_ERR_INVALID;
@@ -269,7 +278,8 @@ extern "C" int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_
   else if (V == 2) bn_stats_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
   else bn_stats_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
   HL_LAUNCH_CHECK("bn_stats_partial_kernel");
-  bn_stats_final_kernel<<<(width * 32 + 255) / 256, 256, 0, st>>>(partial, nblk, x, nrows, nvalid, width, stats);
+  bn_stats_final_kernel<<<(width * 32 + 255) / 256, 256, 0, st>>>(partial, nblk, x, nrows, nvalid, width, stats,
+                                                                    running_mean, running_mean ? running_var : nullptr, momentum);
   HL_LAUNCH_CHECK("bn_stats_final_kernel");
   const int g = ew_grid((int64_t)nrows * (width / V));
   if (V == 4) bn_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);

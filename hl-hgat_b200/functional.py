@@ -421,7 +421,7 @@ def segment_mean(src, seg, scale=None):
 # ---------------------------------------------------------------------------------------------
 class _BnAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, slope, nvalid):
+    def forward(ctx, x, gamma, beta, eps, slope, nvalid, running_mean, running_var, momentum):
         N.require_cuda_f32(x, gamma, beta)
         L = N.lib()
         x, ldx = N.row_major(x)
@@ -431,8 +431,8 @@ class _BnAct(torch.autograd.Function):
         nb = L.hl_bn_workspace(R, F)
         ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
         N.check(L.hl_bn_act_fwd(x.data_ptr(), ldx, R, F, N.ptr(gamma), N.ptr(beta), eps, slope,
-                                y.data_ptr(), y.stride(0), stats.data_ptr(), N.ptr(nvalid), ws.data_ptr(), nb,
-                                N.stream_ptr()), "hl_bn_act_fwd")
+                                y.data_ptr(), y.stride(0), stats.data_ptr(), N.ptr(nvalid), N.ptr(running_mean),
+                                N.ptr(running_var), float(momentum), ws.data_ptr(), nb, N.stream_ptr()), "hl_bn_act_fwd")
         ctx.eps, ctx.slope, ctx.nvalid = eps, slope, nvalid
         ctx.save_for_backward(x, y, gamma, stats)
         ctx.mark_non_differentiable(stats)
@@ -453,10 +453,11 @@ class _BnAct(torch.autograd.Function):
                                 N.ptr(gamma), stats.data_ptr(), ctx.eps, ctx.slope, dx.data_ptr(), dx.stride(0),
                                 dgamma.data_ptr(), dbeta.data_ptr(), N.ptr(ctx.nvalid), ws.data_ptr(), nb,
                                 N.stream_ptr()), "hl_bn_act_bwd")
-        return dx, dgamma, dbeta, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None
 
 
-def bn_act_train(x, gamma, beta, eps=1e-5, slope=0.0, nvalid=None):
+def bn_act_train(x, gamma, beta, eps=1e-5, slope=0.0, nvalid=None, running_mean=None, running_var=None, momentum=0.1):
     """Training-mode BatchNorm1d over rows + (leaky) ReLU; returns (y, stats[2F] = mean | biased var).
-    `nvalid`: optional device int32 scalar -- rows beyond it are padding (excluded, written as zeros)."""
-    return _BnAct.apply(x, gamma, beta, float(eps), float(slope), nvalid)
+    `nvalid`: optional device int32 scalar -- rows beyond it are padding (excluded, written as zeros).
+    running_mean / running_var (optional) are updated in the same launch, like nn.BatchNorm1d."""
+    return _BnAct.apply(x, gamma, beta, float(eps), float(slope), nvalid, running_mean, running_var, momentum)

@@ -243,19 +243,14 @@ def _bn_relu(bn, x, slope=0.0, nvalid=None):
     if not (bn.training or not bn.track_running_stats):
         y = torch.nn.functional.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
         return torch.nn.functional.leaky_relu(y, slope) if slope != 1.0 else y
-    y, stats = F_hl.bn_act_train(x, bn.weight, bn.bias, bn.eps, slope, nvalid)
-    if bn.track_running_stats and bn.training:
+    track = bn.track_running_stats and bn.training
+    if track:
         with torch.no_grad():
-            f = x.shape[1]
             bn.num_batches_tracked += 1
-            m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-            bn.running_mean.mul_(1 - m).add_(stats[:f], alpha=m)
-            if nvalid is None:
-                n = x.shape[0]
-                bn.running_var.mul_(1 - m).add_(stats[f:], alpha=m * n / max(n - 1, 1))
-            else:
-                nf = nvalid.to(torch.float32)
-                bn.running_var.mul_(1 - m).add_(stats[f:] * (m * nf / (nf - 1).clamp(min=1)))
+        m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+        y, _ = F_hl.bn_act_train(x, bn.weight, bn.bias, bn.eps, slope, nvalid, bn.running_mean, bn.running_var, m)
+    else:
+        y, _ = F_hl.bn_act_train(x, bn.weight, bn.bias, bn.eps, slope, nvalid)
     return y
 
 

@@ -200,7 +200,8 @@ int hl_att_gate_bwd(const float* qc, const float* qs, const float* k, const floa
  * Replaces: gnn.BatchNorm / nn.BatchNorm1d + ReLU/LeakyReLU, lib/Hodge_ST_Model.py:580-586,
  * lib/Hodge_Cheb_Conv.py:278-282, and torch.cat lib/Hodge_ST_Model.py:632-633.
  *   y = act( (x - mean) * rsqrt(var_biased + eps) * gamma + beta ),  act: slope 0 = ReLU, 1 = identity
- * stats[0:F] = mean, stats[F:2F] = biased var (both fp32).  running stats are the caller's.
+ * stats[0:F] = mean, stats[F:2F] = biased var (both fp32).  If running_mean/running_var are given they are
+ * updated in the same launch as nn.BatchNorm1d does (momentum, unbiased variance).
  * `nvalid` (device int32, nullable): only rows [0, *nvalid) enter the statistics; rows beyond are
  * padding ("ghost" rows of a fixed-capacity batch replayed from a CUDA graph): y and dx are written
  * as exact zeros there, so they contribute nothing to any later reduction or weight gradient.
@@ -209,6 +210,7 @@ size_t hl_bn_workspace(int32_t nrows, int32_t width);
 int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_t width,
                   const float* gamma, const float* beta, float eps, float slope,
                   float* y, int64_t ld_y, float* stats, const int32_t* nvalid /* device, nullable */,
+                  float* running_mean /* nullable */, float* running_var, float momentum,
                   void* workspace, size_t workspace_bytes, hl_stream_t stream);
 int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64_t ld_y,
                   const float* dy, int64_t ld_dy, int32_t nrows, int32_t width,

@@ -417,3 +417,20 @@ def test_tcgen05_wgrad_vs_fp64(R, fo, fi):
     got = F_hl.wgrad(g, x)
     assert float((got.double() - ref).abs().max()) < 1e-4 * float(ref.abs().max())
     assert torch.equal(F_hl.wgrad(g, x), got)
+
+
+def test_bn_running_stats_match_torch():
+    torch.manual_seed(3)
+    x = torch.randn(777, 48) * 2 + 1
+    ref = torch.nn.BatchNorm1d(48).train()
+    with torch.no_grad():
+        ref.running_mean.normal_()
+        ref.running_var.uniform_(0.5, 2.0)
+    mine = torch.nn.BatchNorm1d(48).to(DEV).train()
+    mine.load_state_dict(ref.state_dict())
+    from hlhgat_b200.lib.Hodge_Cheb_Conv import _bn_relu
+    y = _bn_relu(mine, x.to(DEV), slope=1.0)
+    close(y, ref(x))
+    close(mine.running_mean, ref.running_mean)
+    close(mine.running_var, ref.running_var)
+    assert int(mine.num_batches_tracked) == 1
