@@ -19,6 +19,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_OUT = sys.stdout
+
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
@@ -135,7 +137,7 @@ def run_reference(args, world, rank):
                              "sample": f"{args.steps} training steps on {sample}-graph ZINC-shaped batches "
                                        f"(a bounded sample of the 1024-graph workload), {cores} torch threads"},
             "e2e": {"value": gps, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -284,10 +286,21 @@ def run_ours(args, world, rank, local):
         line["cpu_baseline"] = {"value": gps, "unit": "graphs/s", "cores": cores, "kind": "port",
                                 "sample": "3 training steps (1 warm-up) on 256-graph ZINC-shaped batches, same model, "
                                           f"{cores} torch threads; pure-torch restatement of the reference, not PyG"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
+
+
+def _claim_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on stdout.
+    Keep a private handle to the real stdout and point fd 1 at stderr for everything else."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
+    global _OUT
+    _OUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

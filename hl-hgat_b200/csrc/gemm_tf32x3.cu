@@ -101,6 +101,7 @@ struct GemmParams {
   float* C;
   int64_t ldc;
   int32_t accumulate;
+  int32_t kb_first;         // forward mode: k-blocks taken from the first A operand (the rest from the second)
   int32_t k_per_split;      // wgrad mode: rows of the contraction handled by one blockIdx.z (multiple of 32)
   int64_t split_stride;     // wgrad mode: elements between partial outputs of consecutive splits
 };
@@ -111,7 +112,8 @@ struct GemmParams {
 template <int MODE>
 __global__ void __launch_bounds__(kGmThreads)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
-                   const __grid_constant__ CUtensorMap map_blo, const GemmParams P) {
+                   const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_a2,
+                   const GemmParams P) {
   extern __shared__ __align__(1024) unsigned char gm_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bn = P.bn, stages = P.stages;
@@ -162,7 +164,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         unsigned char* st = base + (size_t)s * stage_bytes;
         if (MODE == 0) {
           gm_mbar_arrive_expect_tx(&full_bar[s], a_bytes + 2 * b_bytes);
-          gm_tma_load_2d(st, &map_a, &full_bar[s], kb * kGmBK, m0);
+          // [A | A2] W^T: the second operand continues the contraction (B is packed [N, K1pad + K2])
+          if (kb < P.kb_first) gm_tma_load_2d(st, &map_a, &full_bar[s], kb * kGmBK, m0);
+          else gm_tma_load_2d(st, &map_a2, &full_bar[s], (kb - P.kb_first) * kGmBK, m0);
           gm_tma_load_2d(st + 2 * a_bytes, &map_bhi, &full_bar[s], kb * kGmBK, n0);
           gm_tma_load_2d(st + 2 * a_bytes + b_bytes, &map_blo, &full_bar[s], kb * kGmBK, n0);
         } else {
@@ -365,14 +369,28 @@ extern "C" int hl_tf32_split(const float* src, int64_t ld_src, int32_t rows, int
   return HL_OK;
 }
 
+extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const float* A2, int64_t lda2, int32_t K2,
+                               const float* Bhi, const float* Blo, int64_t ldb, int32_t M, int32_t N,
+                               const float* bias, float* C, int64_t ldc, int accumulate, hl_stream_t stream);
+
 // returns HL_OK, or 1 when the shape / alignment is not supported (caller uses a library GEMM instead)
 extern "C" int hl_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb,
                               int32_t M, int32_t N, int32_t K, const float* bias, float* C, int64_t ldc,
                               int accumulate, hl_stream_t stream) {
+  return hl_gemm2_tf32x3(A, lda, K, nullptr, 0, 0, Bhi, Blo, ldb, M, N, bias, C, ldc, accumulate, stream);
+}
+
+// C = [A1 | A2] * B^T: B = [N, pad32(K1) + K2] (the columns of the second block start at pad32(K1)).
+extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const float* A2, int64_t lda2, int32_t K2,
+                               const float* Bhi, const float* Blo, int64_t ldb, int32_t M, int32_t N,
+                               const float* bias, float* C, int64_t ldc, int accumulate, hl_stream_t stream) {
   using namespace hl;
-  if (M < 0 || N < 1 || K < 1 || !C) return HL_ERR_INVALID;
+  if (M < 0 || N < 1 || K < 1 || K2 < 0 || !C) return HL_ERR_INVALID;
   if (M == 0) return HL_OK;
-  if (!A || !Bhi || !Blo) return HL_ERR_INVALID;
+  if (!A || !Bhi || !Blo || (K2 > 0 && !A2)) return HL_ERR_INVALID;
+  if (K2 > 0 && (lda2 % 4 != 0 || !aligned_to(A2, 16))) return 1;
+  const int kb_first = (K + kGmBK - 1) / kGmBK;
+  const int Ktot = K2 > 0 ? kb_first * kGmBK + K2 : K;
   // TMA: 16-byte aligned base and row pitch; MMA: N multiple of 16, one N tile of <= 256 columns per CTA
   if (lda % 4 != 0 || ldb % 4 != 0 || !aligned_to(A, 16) || !aligned_to(Bhi, 16) || !aligned_to(Blo, 16)) return 1;
   if (N % 16 != 0) return 1;
@@ -389,19 +407,22 @@ extern "C" int hl_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, con
   if (stages < 2) return 1;
   const size_t smem = stages * stage_bytes + (3 * stages + 2) * sizeof(uint64_t) + 1024;
 
-  CUtensorMap ma, mbh, mbl;
-  if (!make_map(&ma, A, M, K, lda, kGmBM) || !make_map(&mbh, Bhi, N, K, ldb, bn) || !make_map(&mbl, Blo, N, K, ldb, bn))
+  CUtensorMap ma, mbh, mbl, ma2;
+  if (!make_map(&ma, A, M, K, lda, kGmBM) || !make_map(&mbh, Bhi, N, Ktot, ldb, bn) || !make_map(&mbl, Blo, N, Ktot, ldb, bn))
     return 1;
+  if (K2 > 0) { if (!make_map(&ma2, A2, M, K2, lda2, kGmBM)) return 1; }
+  else ma2 = ma;
   static bool configured = false;
   if (!configured) {
     HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   GemmParams P;
-  P.M = M; P.N = N; P.K = K; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
+  P.M = M; P.N = N; P.K = Ktot; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
   P.bias = bias; P.C = C; P.ldc = ldc; P.accumulate = accumulate; P.k_per_split = 0; P.split_stride = 0;
+  P.kb_first = K2 > 0 ? kb_first : 0x7fffffff;
   dim3 grid((M + kGmBM - 1) / kGmBM, ntiles);
-  gemm_tf32x3_kernel<0><<<grid, kGmThreads, smem, as_stream(stream)>>>(ma, mbh, mbl, P);
+  gemm_tf32x3_kernel<0><<<grid, kGmThreads, smem, as_stream(stream)>>>(ma, mbh, mbl, ma2, P);
   HL_LAUNCH_CHECK("gemm_tf32x3_kernel");
   return HL_OK;
 }
@@ -468,7 +489,8 @@ extern "C" int hl_wgrad_tf32x3(const float* g, int64_t ld_g, const float* x, int
   P.bias = nullptr; P.C = reinterpret_cast<float*>(workspace); P.ldc = fi; P.accumulate = 0;
   P.k_per_split = k_per_split; P.split_stride = (int64_t)fo * fi;
   dim3 grid(mtiles, ntiles, splits);
-  gemm_tf32x3_kernel<1><<<grid, kGmThreads, smem, as_stream(stream)>>>(mg, mx, mx, P);
+  P.kb_first = 0;
+  gemm_tf32x3_kernel<1><<<grid, kGmThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
   HL_LAUNCH_CHECK("gemm_tf32x3_kernel<wgrad>");
   const int64_t n = (int64_t)fo * fi;
   gm_split_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, as_stream(stream)>>>(P.C, splits, P.split_stride, fo, fi, dw, ld_dw,

@@ -93,6 +93,36 @@ def dense(a, w, bias=None, out=None, accumulate=False, transpose_w=False):
     return out
 
 
+def dense2(a1, w1, a2, w2, bias=None, out=None, accumulate=False):
+    """out (=|+=) a1 @ w1.T + a2 @ w2.T (+ bias) in ONE tensor-core launch (the sum stays in TMEM)."""
+    L = N.lib()
+    M, k1 = a1.shape
+    k2 = a2.shape[1]
+    n_out = w1.shape[0]
+    ok = (_GEMM_MODE["tensor"] and M > 0 and n_out % 16 == 0 and k1 % 4 == 0 and k2 % 4 == 0
+          and all(t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (a1, a2)))
+    if ok:
+        k1p = (k1 + 31) // 32 * 32
+        kt = k1p + k2
+        hi = torch.zeros((n_out, kt), dtype=torch.float32, device=a1.device)
+        lo = torch.zeros((n_out, kt), dtype=torch.float32, device=a1.device)
+        st = N.stream_ptr()
+        N.check(L.hl_tf32_split(w1.data_ptr(), w1.stride(0), n_out, k1, 0, hi.data_ptr(), lo.data_ptr(), kt, st), "hl_tf32_split")
+        N.check(L.hl_tf32_split(w2.data_ptr(), w2.stride(0), n_out, k2, 0, hi[:, k1p:].data_ptr(), lo[:, k1p:].data_ptr(), kt, st),
+                "hl_tf32_split")
+        if out is None:
+            out = torch.empty((M, n_out), dtype=torch.float32, device=a1.device)
+            accumulate = False
+        rc = L.hl_gemm2_tf32x3(a1.data_ptr(), a1.stride(0), k1, a2.data_ptr(), a2.stride(0), k2, hi.data_ptr(), lo.data_ptr(), kt,
+                               M, n_out, N.ptr(bias), out.data_ptr(), out.stride(0), 1 if accumulate else 0, st)
+        if rc == 0:
+            return out
+        if rc != 1:
+            N.check(rc, "hl_gemm2_tf32x3")
+    out = dense(a1, w1, bias, out=out, accumulate=accumulate)
+    return dense(a2, w2, None, out=out, accumulate=True)
+
+
 def wgrad(g, x, out=None):
     """dW[Fo,Fi] = g[R,Fo]^T x[R,Fi] (deterministic split-row reduction); `out` may be a column slice."""
     L = N.lib()
@@ -142,8 +172,7 @@ class _Linear(torch.autograd.Function):
             y = dense(xa, weight, bias)
         else:
             xb = xb.contiguous() if xb.stride(1) != 1 else xb
-            y = dense(xa, weight[:, :d], bias)
-            dense(xb, weight[:, d:], None, out=y, accumulate=True)
+            y = dense2(xa, weight[:, :d], xb, weight[:, d:], bias)
         ctx.save_for_backward(xa, xb, weight)
         ctx.has_bias = bias is not None
         return y
@@ -184,9 +213,15 @@ class _PolyConv(torch.autograd.Function):
         R, width = x.shape
         (t,) = poly_basis_fwd(family, K, [op], [x], width)
         xv = x.view(-1, inner)
-        out = dense(xv, weights[0], bias)
-        for k in range(1, K):
-            dense(t[k - 1].view(-1, inner), weights[k], None, out=out, accumulate=True)
+        if K == 1:
+            out = dense(xv, weights[0], bias)
+        else:
+            out = dense2(xv, weights[0], t[0].view(-1, inner), weights[1], bias)
+            for k in range(2, K, 2):
+                if k + 1 < K:
+                    dense2(t[k - 1].view(-1, inner), weights[k], t[k].view(-1, inner), weights[k + 1], None, out=out, accumulate=True)
+                else:
+                    dense(t[k - 1].view(-1, inner), weights[k], None, out=out, accumulate=True)
         ctx.op, ctx.family, ctx.inner, ctx.has_bias = op, family, inner, bias is not None
         ctx.save_for_backward(x, t, *weights)
         return out

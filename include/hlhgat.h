@@ -233,6 +233,12 @@ int hl_tf32_split(const float* src, int64_t ld_src, int32_t rows, int32_t cols, 
 int hl_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb,
                    int32_t M, int32_t N, int32_t K, const float* bias, float* C, int64_t ldc,
                    int accumulate, hl_stream_t stream);
+/* C = [A | A2] * B^T in one launch: the contraction continues over a second row-major operand (the next
+ * polynomial order T_1 after T_0 = x, or [transferred | own] of the NodeEdgeInt MLP), so the partial sum never
+ * leaves TMEM.  B is packed [N, pad32(K) + K2] (block 2 starts at column pad32(K); padding must be zero). */
+int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const float* A2, int64_t lda2, int32_t K2,
+                    const float* Bhi, const float* Blo, int64_t ldb, int32_t M, int32_t N,
+                    const float* bias, float* C, int64_t ldc, int accumulate, hl_stream_t stream);
 /* Weight gradient on the same tensor-core path: dw[fo,fi] (=|+=) g[R,fo]^T x[R,fi].  Both operands are
  * consumed MN-major straight from their row-major storage ({32 x 32} TMA boxes, no transposes), split into
  * hi/lo inside the kernel, the R rows are divided over CTAs and the partial tiles are summed in a fixed
