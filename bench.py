@@ -140,6 +140,19 @@ def run_reference(args, world, rank):
     print(json.dumps(line), file=_OUT, flush=True)
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the SpMM launch from the committed ncu capture."""
+    try:
+        tot = 0.0
+        for ln in open(os.path.join(ROOT, "profiles", "r1_spmm_v3_staged_full.txt")):
+            if ln.startswith("dram__bytes_read.sum") or ln.startswith("dram__bytes_write.sum"):
+                val, unit = ln.split("=")[1].split()[:2]
+                tot += float(val) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
+        return tot or None
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 # roofline leg: the polynomial SpMM kernel on an operator stack larger than L2
 # ------------------------------------------------------------------------------------------------
@@ -172,9 +185,10 @@ def spmm_roofline(dev, batch_dev, reps=16, width=64, iters=20):
     ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
     pk, kind = peaks()
     ach = alg_bytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "poly_spmm_kernel<4,1> (fused L0+L1, Laguerre first order)",
+    return {"bound": "hbm", "kernel": "poly_spmm_staged_kernel<LAGUERRE_FIRST> (fused L0+L1 launch, cp.async.bulk ring)",
             "achieved": ach, "peak": pk["hbm_gbs"], "peak_kind": f"{kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
-            "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+            "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic_bytes(),
+            "traffic_source": "profiles/r1_spmm_v3_staged_full.txt (ncu --set full of tools/spmm_probe.py, same operator stack)",
             "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": ms * 1e3,
             "workload": f"ZINC-shaped B={BATCH}x{reps} block-diagonal, rows {rows_tot}, nnz {nnz_tot}, F={width}; "
                         "inputs+outputs > L2"}
@@ -272,7 +286,8 @@ def run_ours(args, world, rank, local):
                              "and consecutive steps use different batches",
                        "execution": "whole step (CSR bucketing + forward + backward) replayed as one CUDA graph on batches padded "
                                     f"to a fixed capacity ({cap.nodes} nodes / {cap.edges} edges, ~2% ghost rows), then all-reduce + fused Adam graph",
-                       "gemm": "dense Theta/MLP GEMMs via cuBLAS fp32 (torch.mm); all sparse/segment/BN kernels hand-written"},
+                       "gemm": "dense Theta/MLP transforms + data/weight gradients: hand-written tcgen05 3xTF32 kernels (fp32-accurate); "
+                               "cuBLAS fp32 only for the 10-column edge input of the first conv"},
             "e2e": {"value": e2e, "unit": "graphs/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "gpu_launches_note": "libhlhgat kernels inside the replayed graph x steps (cuBLAS/ATen launches not counted)",
