@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -397,13 +398,22 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
   // Column tile: as wide as possible (<= 256 columns, multiple of 16; TMA zero-fills the overhang).  Narrower
   // tiles with two co-resident CTAs per SM were measured slower (A re-read from L2, N=64 MMAs): 181 vs 155 us
   // on [24000,1408]x[1408,256].
-  const int ntiles = (N + 255) / 256;
+  // Column tile: <= 128 columns (3 ring stages of 64 KB) measured best: 141 us vs 155 us (256 columns, 2 stages)
+  // vs 217 us (64 columns) on [24000,1408]x[1408,256].  An L2 prefetch of the activations 8 k-blocks ahead made
+  // no difference (the ring is not DRAM-latency bound).  HL_GEMM_MAX_BN overrides for experiments.
+  static int max_bn = 0;
+  if (max_bn == 0) {
+    const char* e = getenv("HL_GEMM_MAX_BN");
+    max_bn = e ? atoi(e) : 128;
+    if (max_bn < 16 || max_bn > 256) max_bn = 128;
+  }
+  const int ntiles = (N + max_bn - 1) / max_bn;
   const int bn = ((N + ntiles - 1) / ntiles + 15) / 16 * 16;
   int tmem_cols = 32;
   while (tmem_cols < bn) tmem_cols <<= 1;
   const size_t stage_bytes = 2 * (size_t)kGmBM * kGmBK * 4 + 2 * (size_t)bn * kGmBK * 4;
   int stages = (int)((200 * 1024) / stage_bytes);
-  if (stages > 4) stages = 4;
+  if (stages > 6) stages = 6;
   if (stages < 2) return 1;
   const size_t smem = stages * stage_bytes + (3 * stages + 2) * sizeof(uint64_t) + 1024;
 
