@@ -392,3 +392,194 @@ class HL_HGCNN_zinc_dense_int3_pyr(nn.Module):
         for i in range(len(self.mlp_channels)):
             x = getattr(self, f"mlp{i}")(x)
         return self.out(x)
+
+
+# --------------------------------------------------------------------------------------
+# the other BASELINE.json callers: TSP pyr, CIFAR10-superpixel attpool, peptides-func attpool
+# --------------------------------------------------------------------------------------
+def _seg_ids(counts):
+    counts = torch.as_tensor(counts)
+    return torch.repeat_interleave(torch.arange(len(counts)), counts)
+
+
+def _build_stack(self, K, K_init, dropout_ratio):
+    """HL_init_conv + NEInt{i}{j} / NEConv{i}{j} (identical in all four model classes, e.g.
+    lib/Hodge_ST_Model.py:768-802); returns the width of the dense-connection buffer."""
+    f0 = self.filters[0]
+    self.HL_init_conv = NEConvBlock(self.node_dim, self.edge_dim, f0, K_init, dropout_ratio)
+    fin = f0
+    self._stage_width = []
+    for i, fout in enumerate(self.filters):
+        for j in range(self.channels[i]):
+            setattr(self, f"NEInt{i}{j}", NodeEdgeInt(d=fin, dv=fout))
+            setattr(self, f"NEConv{i}{j}", NEConvBlock(fout, fout, fout, K, dropout_ratio))
+            fin = fin + fout
+        self._stage_width.append(fin)
+    return fin
+
+
+def _pool_positions(datas):
+    """lib/Hodge_ST_Model.py:1027-1036: float cluster ids of level 0 (column 0 of x_t / x_s) offset by the
+    level-1 graph sizes."""
+    nb, sb = _seg_ids(datas[0].num_node1), _seg_ids(datas[0].num_edge1)
+    n_ahead = torch.cumsum(torch.cat([torch.zeros(1), datas[1].num_node1.float()]), 0, dtype=torch.long)[:-1]
+    s_ahead = torch.cumsum(torch.cat([torch.zeros(1), datas[1].num_edge1.float()]), 0, dtype=torch.long)[:-1]
+    return (datas[0].x_t[:, 0] + n_ahead[nb]).view(-1, 1), (datas[0].x_s[:, 0] + s_ahead[sb]).view(-1, 1)
+
+
+def _cluster_mean(x_t0, x_s0, pos_t, pos_s):
+    """lib/Hodge_ST_Model.py:1063-1067."""
+    x_t0 = scatter_mean(x_t0, pos_t.to(torch.long))
+    keep = ~torch.isinf(pos_s).view(-1)
+    return x_t0, scatter_mean(x_s0[keep], pos_s[keep].to(torch.long))
+
+
+class _HeadMlp(nn.Module):
+    def _build_head(self, num_classes, dropout_ratio_mlp):
+        m_in = self.filters[-1] * 2
+        for i, m_out in enumerate(self.mlp_channels):
+            setattr(self, f"mlp{i}", nn.Sequential(nn.Linear(m_in, m_out), nn.BatchNorm1d(m_out),
+                                                   nn.ReLU(), nn.Dropout(dropout_ratio_mlp)))
+            m_in = m_out
+        self.out = nn.Linear(m_in, num_classes)
+
+    def _head(self, x):
+        for i in range(len(self.mlp_channels)):
+            x = getattr(self, f"mlp{i}")(x)
+        return self.out(x)
+
+
+class _SeqConv(nn.Module):
+    """gnn.Sequential([(HodgeLaguerreConv(K=1), ..), (gnn.BatchNorm), ReLU, Dropout]) of the TSP head
+    (lib/Hodge_ST_Model.py:806-817): children module_0 (conv) [, module_1 (BN)]."""
+
+    def __init__(self, fin, fout, with_bn, dropout=0.0):
+        super().__init__()
+        self.module_0 = HodgeLaguerreConv(fin, fout, 1)
+        if with_bn:
+            self.module_1 = GraphBatchNorm(fout)
+        self.with_bn, self.drop = with_bn, nn.Dropout(dropout)
+
+    def forward(self, x, ei, ew):
+        x = self.module_0(x, ei, ew)
+        return self.drop(torch.relu(self.module_1(x))) if self.with_bn else x
+
+
+class HL_HGCNN_TSP_dense_int3_pyr(nn.Module):
+    """lib/Hodge_ST_Model.py:756-852: per-edge output; readout cat[x_s, |B1^T x_t|/2] (:848-849) -> K=1
+    conv (+BN+ReLU) -> K=1 conv, times edge_mask (= data.x_s[:,1:])."""
+
+    def __init__(self, channels=(2, 2, 2), filters=(64, 128, 256), mlp_channels=(), K=2, node_dim=2, edge_dim=1,
+                 num_classes=1, dropout_ratio=0.0, dropout_ratio_mlp=0.0, keig=20):
+        super().__init__()
+        self.channels, self.filters, self.mlp_channels = list(channels), list(filters), list(mlp_channels)
+        self.node_dim, self.edge_dim = node_dim, edge_dim
+        _build_stack(self, K, K, dropout_ratio)
+        m_in = self.filters[-1] * 2
+        if len(self.mlp_channels) == 1:
+            self.mlp = _SeqConv(m_in, self.mlp_channels[0], True, dropout_ratio)
+            m_in = self.mlp_channels[0]
+        self.out = _SeqConv(m_in, num_classes, False)
+
+    def forward(self, data):
+        ei_t, ew_t, ei_s, ew_s = data.edge_index_t, data.edge_weight_t, data.edge_index_s, data.edge_weight_s
+        x_s, edge_mask = data.x_s[:, :1], data.x_s[:, 1:]
+        x_t, x_s = self.HL_init_conv(data.x_t, ei_t, ew_t, x_s, ei_s, ew_s)
+        x_t0, x_s0 = x_t, x_s
+        par = adj2par1(data.edge_index, x_t.shape[0], x_s.shape[0], x_t.dtype)
+        D = degree(data.edge_index.view(-1), x_t.shape[0], dtype=x_t.dtype) + 1e-6
+        for i in range(len(self.channels)):
+            for j in range(self.channels[i]):
+                x_t, x_s = getattr(self, f"NEInt{i}{j}")(x_t0, x_s0, par, D)
+                x_t, x_s = getattr(self, f"NEConv{i}{j}")(x_t, ei_t, ew_t, x_s, ei_s, ew_s)
+                x_t0 = torch.cat([x_t0, x_t], -1)
+                x_s0 = torch.cat([x_s0, x_s], -1)
+        x_t2s = torch.sparse.mm(par.transpose(0, 1), x_t).abs() / 2
+        x_s = torch.cat([x_s, x_t2s], -1)
+        if len(self.mlp_channels) == 1:
+            x_s = self.mlp(x_s, ei_s, ew_s)
+        return self.out(x_s, ei_s, ew_s) * edge_mask, _seg_ids(data.num_edge1)
+
+
+class _AttPoolBase(_HeadMlp):
+    def _level(self, datas, k, x_t0, x_s0):
+        d = datas[k]
+        par = adj2par1(d.edge_index, x_t0.shape[0], x_s0.shape[0], x_t0.dtype)
+        D = degree(d.edge_index.view(-1), x_t0.shape[0], dtype=x_t0.dtype) + 1e-6
+        return par, D, d.edge_index_t, d.edge_weight_t, d.edge_index_s, d.edge_weight_s
+
+    def _readout(self, datas, x_t, x_s, last_stage):
+        d = datas[min(last_stage, 1)]
+        nb, sb = _seg_ids(d.num_node1), _seg_ids(d.num_edge1)
+        return torch.cat([global_mean_pool(x_s, sb, len(d.num_edge1)), global_mean_pool(x_t, nb, len(d.num_node1))], -1)
+
+
+class HL_HGCNN_CIFAR10SP_dense_int3_attpool(_AttPoolBase):
+    """lib/Hodge_ST_Model.py:958-1091.  As written in the reference the gate only rescales the stage
+    outputs x_t / x_s (:1061-1062), which the next stage overwrites: the dense-connection buffers are
+    pooled UNGATED (:1064-1067) and NEAtt receives no gradient unless pool_loc is the last stage."""
+
+    def __init__(self, channels=(2, 2, 2), filters=(64, 128, 256), mlp_channels=(), K=2, node_dim=5, l=0.5, edge_dim=4,
+                 num_classes=10, dropout_ratio=0.0, dropout_ratio_mlp=0.0, pool_loc=0, keig=10):
+        super().__init__()
+        self.channels, self.filters, self.mlp_channels = list(channels), list(filters), list(mlp_channels)
+        self.node_dim, self.edge_dim, self.pool_loc = node_dim + keig, edge_dim + keig, pool_loc
+        _build_stack(self, K, 1, dropout_ratio)
+        f = self.filters[pool_loc]
+        setattr(self, f"NEAtt{pool_loc}", NodeEdgeInt(d=f, dv=f, only_att=True, sigma=nn.ReLU(), l=l))
+        self._build_head(num_classes, dropout_ratio_mlp)
+
+    def forward(self, datas, if_att=False):
+        pos_t, pos_s = _pool_positions(datas)
+        par, D, ei_t, ew_t, ei_s, ew_s = self._level(datas, 0, datas[0].x_t, datas[0].x_s)
+        x_t, x_s = self.HL_init_conv(datas[0].x_t[:, 1:], ei_t, ew_t, datas[0].x_s[:, 1:], ei_s, ew_s)
+        x_t0, x_s0 = x_t, x_s
+        att_t = att_s = None
+        for i in range(len(self.channels)):
+            for j in range(self.channels[i]):
+                x_t, x_s = getattr(self, f"NEInt{i}{j}")(x_t0, x_s0, par, D)
+                x_t, x_s = getattr(self, f"NEConv{i}{j}")(x_t, ei_t, ew_t, x_s, ei_s, ew_s)
+                x_t0 = torch.cat([x_t0, x_t], -1)
+                x_s0 = torch.cat([x_s0, x_s], -1)
+            if i == self.pool_loc:
+                att_t, att_s = getattr(self, f"NEAtt{i}")(x_t, x_s, par, D)
+                att_t, att_s = att_t / att_t.max(), att_s / att_s.max()
+                x_t, x_s = x_t * att_t, x_s * att_s
+                x_t0, x_s0 = _cluster_mean(x_t0, x_s0, pos_t, pos_s)
+                par, D, ei_t, ew_t, ei_s, ew_s = self._level(datas, 1, x_t0, x_s0)
+        out = self._head(self._readout(datas, x_t, x_s, len(self.channels) - 1))
+        return (out, att_t, att_s) if if_att else out
+
+
+class HL_HGCNN_pepfunc_dense_int3_attpool(_AttPoolBase):
+    """main_pepfunc_HL_HGCNN_dense_int3_attpool.py:36-168: a sigmoid gate after EVERY stage on the full
+    dense-connection buffer (:131-134), cluster pooling after stage pool_loc (:137-148)."""
+
+    def __init__(self, channels=(2, 2, 2, 2), filters=(64, 128, 256, 512), mlp_channels=(), K=2, node_dim=9, edge_dim=3,
+                 num_classes=10, dropout_ratio=0.0, dropout_ratio_mlp=0.0, pool_loc=0, keig=20):
+        super().__init__()
+        self.channels, self.filters, self.mlp_channels = list(channels), list(filters), list(mlp_channels)
+        self.node_dim, self.edge_dim, self.pool_loc = node_dim + keig, edge_dim + keig, pool_loc
+        _build_stack(self, K, 1, dropout_ratio)
+        for i, f in enumerate(self.filters):
+            setattr(self, f"NEAtt{i}", NodeEdgeInt(d=self._stage_width[i], dv=f, only_att=True, l=0.5))
+        self._build_head(num_classes, dropout_ratio_mlp)
+
+    def forward(self, datas, if_att=False):
+        pos_t, pos_s = _pool_positions(datas)
+        par, D, ei_t, ew_t, ei_s, ew_s = self._level(datas, 0, datas[0].x_t, datas[0].x_s)
+        x_t, x_s = self.HL_init_conv(datas[0].x_t[:, 1:], ei_t, ew_t, datas[0].x_s[:, 1:], ei_s, ew_s)
+        x_t0, x_s0 = x_t, x_s
+        for i in range(len(self.channels)):
+            for j in range(self.channels[i]):
+                x_t, x_s = getattr(self, f"NEInt{i}{j}")(x_t0, x_s0, par, D)
+                x_t, x_s = getattr(self, f"NEConv{i}{j}")(x_t, ei_t, ew_t, x_s, ei_s, ew_s)
+                x_t0 = torch.cat([x_t0, x_t], -1)
+                x_s0 = torch.cat([x_s0, x_s], -1)
+            att_t, att_s = getattr(self, f"NEAtt{i}")(x_t0, x_s0, par, D)
+            x_t0, x_s0 = x_t0 * att_t, x_s0 * att_s
+            if i == self.pool_loc:
+                x_t0, x_s0 = _cluster_mean(x_t0, x_s0, pos_t, pos_s)
+                par, D, ei_t, ew_t, ei_s, ew_s = self._level(datas, 1, x_t0, x_s0)
+        out = self._head(self._readout(datas, x_t, x_s, len(self.channels) - 1))
+        return (out, att_t, att_s) if if_att else out

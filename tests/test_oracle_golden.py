@@ -177,3 +177,41 @@ def test_gradcheck_fp64():
     conv = _conv(c).double()
     x = c["x"].double().requires_grad_(True)
     assert torch.autograd.gradcheck(lambda v: conv(v, c["edge_index"], c["edge_weight"].double()), (x,))
+
+
+# --------------------------------------------------------------------------------------
+# the TSP / CIFAR10-superpixel / peptides-func callers (tests/golden/make_golden_models.py)
+# --------------------------------------------------------------------------------------
+def _check_grads(model, loss, ref_grads):
+    g = torch.autograd.grad(loss, list(model.parameters()), allow_unused=True)
+    for (n, _), t in zip(model.named_parameters(), g):
+        ref = ref_grads[n]
+        assert (t is None) == (ref is None), n
+        if t is not None:            # (a bias in front of a BatchNorm has a zero true gradient: rounding noise up to ~7e-6)
+            assert torch.allclose(t, ref, rtol=1e-4, atol=max(1e-5, 2e-5 * float(ref.abs().max()))), n
+
+
+def test_tsp_model_matches_reference():
+    c = load_golden("models.pt")["tsp"]
+    model = O.HL_HGCNN_TSP_dense_int3_pyr(**c["ctor"])
+    model.load_state_dict(c["state"], strict=True)
+    model.train()
+    pred, s_batch = model(SimpleNamespace(**c["batch"]))
+    assert torch.allclose(pred, c["pred"], rtol=1e-5, atol=1e-5)
+    assert s_batch.numel() == pred.shape[0]
+    _check_grads(model, (pred * c["w"]).sum() / pred.shape[0], c["grads"])
+
+
+@pytest.mark.parametrize("name", ["cifar", "pepfunc"])
+def test_attpool_models_match_reference(name):
+    c = load_golden("models.pt")[name]
+    cls = {"cifar": O.HL_HGCNN_CIFAR10SP_dense_int3_attpool, "pepfunc": O.HL_HGCNN_pepfunc_dense_int3_attpool}[name]
+    model = cls(**c["ctor"])
+    model.load_state_dict(c["state"], strict=True)
+    model.train()
+    datas = [SimpleNamespace(**d) for d in c["datas"]]
+    pred, att_t, att_s = model(datas, if_att=True)
+    assert torch.allclose(pred, c["pred"], rtol=1e-5, atol=1e-5)
+    assert torch.allclose(att_t, c["att_t"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(att_s, c["att_s"], rtol=1e-5, atol=1e-6)
+    _check_grads(model, (pred * c["w"]).sum(), c["grads"])
