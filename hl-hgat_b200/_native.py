@@ -47,6 +47,8 @@ _SIGNATURES = {
     "hl_poly_basis_bwd": (C.c_int, [C.c_int, C.c_int, C.POINTER(ConvSide), C.c_int, _i32, _vp]),
     "hl_segment_reduce": (C.c_int, [_vp, _vp, _i32, _vp, _i64, _vp, _vp, _i64, _i32, C.c_int, _vp, _f32, _vp]),
     "hl_endpoint_gather": (C.c_int, [_vp, _vp, _i32, _vp, _i64, _vp, _vp, _i64, _i32, _f32, _vp]),
+    "hl_boundary_absdiff_fwd": (C.c_int, [_vp, _vp, _i32, _vp, _i64, _vp, _i64, _i32, _f32, _vp]),
+    "hl_boundary_absdiff_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _f32, _vp]),
     "hl_owner_gather": (C.c_int, [_vp, _i32, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i32, _vp]),
     "hl_att_gate_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _f32, C.c_int, _vp, _vp]),
     "hl_att_gate_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, C.c_int, _vp, _vp, _vp, _vp]),

@@ -134,6 +134,66 @@ endpoint_gather_kernel(const int32_t* __restrict__ tail, const int32_t* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
+// dst[e,:] = cscale * | src[head[e],:] - src[tail[e],:] |      (signed boundary B1^T, then abs)
+// ---------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256)
+boundary_absdiff_fwd_kernel(const int32_t* __restrict__ tail, const int32_t* __restrict__ head, int32_t nedges,
+                            const float* __restrict__ src, int64_t ld_src, float* __restrict__ dst, int64_t ld_dst,
+                            int32_t chunks, float cscale) {
+  const int64_t total = (int64_t)nedges * chunks;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(idx / chunks);
+    const int col = (int)(idx - (int64_t)e * chunks) * V;
+    Pack<V> a = ld_pack<V>(src + (int64_t)__ldg(tail + e) * ld_src + col);
+    Pack<V> b = ld_pack<V>(src + (int64_t)__ldg(head + e) * ld_src + col);
+    Pack<V> o;
+#pragma unroll
+    for (int i = 0; i < V; ++i) o.v[i] = __fmul_rn(cscale, fabsf(__fadd_rn(b.v[i], -a.v[i])));
+    st_pack<V>(dst + (int64_t)e * ld_dst + col, o);
+  }
+}
+
+// dsrc[n,:] = cscale * sum_{e incident to n, ascending e} s(n,e) * sgn(src[head_e]-src[tail_e]) * g[e,:],
+// s(n,e) = +1 if n is the head of e, -1 if it is the tail.  One lane group per node; no atomics.
+template <int V>
+__global__ void __launch_bounds__(256)
+boundary_absdiff_bwd_kernel(const int32_t* __restrict__ inc_rowptr, const int32_t* __restrict__ inc_edge,
+                            const int32_t* __restrict__ tail, const int32_t* __restrict__ head, int32_t nnodes,
+                            const float* __restrict__ src, int64_t ld_src, const float* __restrict__ g, int64_t ld_g,
+                            float* __restrict__ dsrc, int64_t ld_dsrc, int32_t width, int32_t G, float cscale) {
+  const int rows_per_block = 256 / G;
+  const int gl = threadIdx.x & (G - 1);
+  const int n = blockIdx.x * rows_per_block + (int)(threadIdx.x / G);
+  if (n >= nnodes) return;
+  const int start = __ldg(inc_rowptr + n), end = __ldg(inc_rowptr + n + 1);
+  for (int col = gl * V; col < width; col += G * V) {
+    Pack<V> acc;
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc.v[i] = 0.f;
+    for (int p = start; p < end; ++p) {
+      const int e = __ldg(inc_edge + p);
+      const int t = __ldg(tail + e), h = __ldg(head + e);
+      if (t == h) continue;                                   // self-pair (ghost padding): B1 column is zero
+      const float s = (h == n) ? 1.f : -1.f;
+      Pack<V> a = ld_pack<V>(src + (int64_t)t * ld_src + col);
+      Pack<V> b = ld_pack<V>(src + (int64_t)h * ld_src + col);
+      Pack<V> gv = ld_pack<V>(g + (int64_t)e * ld_g + col);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float d = __fadd_rn(b.v[i], -a.v[i]);
+        const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+        acc.v[i] = __fadd_rn(acc.v[i], s * sg * gv.v[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc.v[i] = __fmul_rn(cscale, acc.v[i]);
+    st_pack<V>(dsrc + (int64_t)n * ld_dsrc + col, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // dsrc[m,:] = g[owner[m],:] * w_m * scale_m ; dscale[m] = w_m <g[owner[m],:], src[m,:]>
 // ---------------------------------------------------------------------------------------------
 template <int V>
@@ -292,6 +352,44 @@ extern "C" int hl_endpoint_gather(const int32_t* tail, const int32_t* head, int3
   else if (V == 2) endpoint_gather_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(tail, head, nedges, src, ld_src, node_rcp, dst, ld_dst, chunks, cscale);
   else endpoint_gather_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(tail, head, nedges, src, ld_src, node_rcp, dst, ld_dst, chunks, cscale);
   HL_LAUNCH_CHECK("endpoint_gather_kernel");
+  return HL_OK;
+}
+
+extern "C" int hl_boundary_absdiff_fwd(const int32_t* tail, const int32_t* head, int32_t nedges,
+                                       const float* src, int64_t ld_src, float* dst, int64_t ld_dst,
+                                       int32_t width, float cscale, hl_stream_t stream) {
+  using namespace hl;
+  if (nedges < 0 || width < 1) return HL_ERR_INVALID;
+  if (nedges == 0) return HL_OK;
+  if (!tail || !head || !src || !dst) return HL_ERR_INVALID;
+  int V = vec_for(src, ld_src, width, 4);
+  V = min(V, vec_for(dst, ld_dst, width, V));
+  const int chunks = width / V;
+  const int grid = grid_for((int64_t)nedges * chunks, 256);
+  if (V == 4) boundary_absdiff_fwd_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(tail, head, nedges, src, ld_src, dst, ld_dst, chunks, cscale);
+  else if (V == 2) boundary_absdiff_fwd_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(tail, head, nedges, src, ld_src, dst, ld_dst, chunks, cscale);
+  else boundary_absdiff_fwd_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(tail, head, nedges, src, ld_src, dst, ld_dst, chunks, cscale);
+  HL_LAUNCH_CHECK("boundary_absdiff_fwd_kernel");
+  return HL_OK;
+}
+
+extern "C" int hl_boundary_absdiff_bwd(const int32_t* inc_rowptr, const int32_t* inc_edge,
+                                       const int32_t* tail, const int32_t* head, int32_t nnodes,
+                                       const float* src, int64_t ld_src, const float* g, int64_t ld_g,
+                                       float* dsrc, int64_t ld_dsrc, int32_t width, float cscale, hl_stream_t stream) {
+  using namespace hl;
+  if (nnodes < 0 || width < 1) return HL_ERR_INVALID;
+  if (nnodes == 0) return HL_OK;
+  if (!inc_rowptr || !inc_edge || !tail || !head || !src || !g || !dsrc) return HL_ERR_INVALID;
+  int V = vec_for(src, ld_src, width, 4);
+  V = min(V, vec_for(g, ld_g, width, V));
+  V = min(V, vec_for(dsrc, ld_dsrc, width, V));
+  const int G = group_lanes(width, V);
+  const int grid = (nnodes + 256 / G - 1) / (256 / G);
+  if (V == 4) boundary_absdiff_bwd_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(inc_rowptr, inc_edge, tail, head, nnodes, src, ld_src, g, ld_g, dsrc, ld_dsrc, width, G, cscale);
+  else if (V == 2) boundary_absdiff_bwd_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(inc_rowptr, inc_edge, tail, head, nnodes, src, ld_src, g, ld_g, dsrc, ld_dsrc, width, G, cscale);
+  else boundary_absdiff_bwd_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(inc_rowptr, inc_edge, tail, head, nnodes, src, ld_src, g, ld_g, dsrc, ld_dsrc, width, G, cscale);
+  HL_LAUNCH_CHECK("boundary_absdiff_bwd_kernel");
   return HL_OK;
 }
 

@@ -350,6 +350,40 @@ def node_to_edge(x_t, inc):
     return _NodeToEdge.apply(x_t, inc)
 
 
+class _BoundaryAbsDiff(torch.autograd.Function):
+    """|B1^T x_t| / 2 per edge (lib/Hodge_ST_Model.py:848, the TSP readout)."""
+
+    @staticmethod
+    def forward(ctx, x_t, inc):
+        N.require_cuda_f32(x_t)
+        x_t, ld = N.row_major(x_t)
+        width = x_t.shape[1]
+        out = torch.empty((inc.num_edges, width), dtype=torch.float32, device=x_t.device)
+        N.check(N.lib().hl_boundary_absdiff_fwd(inc.tail.data_ptr(), inc.head.data_ptr(), inc.num_edges, x_t.data_ptr(), ld,
+                                                out.data_ptr(), out.stride(0), width, 0.5, N.stream_ptr()),
+                "hl_boundary_absdiff_fwd")
+        ctx.inc, ctx.ld = inc, ld
+        ctx.save_for_backward(x_t)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x_t,) = ctx.saved_tensors
+        inc = ctx.inc
+        g, ldg = N.row_major(g)
+        width = x_t.shape[1]
+        dx = torch.empty((inc.num_nodes, width), dtype=torch.float32, device=g.device)
+        N.check(N.lib().hl_boundary_absdiff_bwd(inc.rowptr.data_ptr(), inc.edge.data_ptr(), inc.tail.data_ptr(),
+                                                inc.head.data_ptr(), inc.num_nodes, x_t.data_ptr(), ctx.ld,
+                                                g.data_ptr(), ldg, dx.data_ptr(), dx.stride(0), width, 0.5, N.stream_ptr()),
+                "hl_boundary_absdiff_bwd")
+        return dx, None
+
+
+def boundary_absdiff(x_t, inc):
+    return _BoundaryAbsDiff.apply(x_t, inc)
+
+
 # ---------------------------------------------------------------------------------------------
 # attention gate, cluster pooling, per-graph readout
 # ---------------------------------------------------------------------------------------------

@@ -73,3 +73,221 @@ class HL_HGCNN_zinc_dense_int3_pyr(nn.Module):
         if if_final_layer:
             return x, self.out(x)
         return self.out(x)
+
+
+# ---------------------------------------------------------------------------------------------
+# the other BASELINE.json callers (TSP pyr, CIFAR10-superpixel attpool, peptides-func attpool)
+# ---------------------------------------------------------------------------------------------
+def _build_stack(self, K, K_init, dropout_ratio):
+    """HL_init_conv + NEInt{i}{j} / NEConv{i}{j}: identical in all model classes of the reference
+    (e.g. lib/Hodge_ST_Model.py:768-802).  Records the dense-connection width after every stage."""
+    f0 = self.filters[0]
+    self.HL_init_conv = NEConv(self.node_dim, self.edge_dim, f0, K_init, dropout_ratio)
+    fin = f0
+    self._stage_width = []
+    for i, fout in enumerate(self.filters):
+        for j in range(self.channels[i]):
+            setattr(self, f"NEInt{i}{j}", NodeEdgeInt(d=fin, dv=fout))
+            setattr(self, f"NEConv{i}{j}", NEConv(fout, fout, fout, K, dropout_ratio))
+            fin = fin + fout
+        self._stage_width.append(fin)
+
+
+class _Level:
+    """Device-side tables of one coarsening level of a batch: operators, incidence, degree, segments."""
+
+    def __init__(self, d, n, e, eps, device):
+        self.n, self.e = n, e
+        self.op_t = operator_for(d.edge_index_t.to(device), d.edge_weight_t.to(device), n)
+        self.op_s = operator_for(d.edge_index_s.to(device), d.edge_weight_s.to(device), e)
+        self.inc = incidence_for(d.edge_index.to(device), n)
+        D = getattr(d, "D", None)
+        self.D = (self.inc.degree() + eps) if D is None else D.to(device)   # degree(edge_index.view(-1), n) + 1e-6
+        self.nv = (getattr(d, "n_valid_nodes", None), getattr(d, "n_valid_edges", None))
+        self.nv_g = getattr(d, "n_valid_graphs", None)
+        self._d, self._device = d, device
+
+    def segments(self):
+        d, dev = self._d, self._device
+        return (F_hl.Segments.from_counts(torch.as_tensor(d.num_node1, device=dev), total=self.n),
+                F_hl.Segments.from_counts(torch.as_tensor(d.num_edge1, device=dev), total=self.e))
+
+
+def _stage(self, i, lv, x_t0, x_s0):
+    x_t = x_s = None
+    for j in range(self.channels[i]):
+        x_t, x_s = getattr(self, f"NEInt{i}{j}")(x_t0, x_s0, lv.inc, lv.D, lv.nv)
+        x_t, x_s = getattr(self, f"NEConv{i}{j}")(x_t, lv.op_t, None, x_s, lv.op_s, None, lv.nv)
+        x_t0 = torch.cat([x_t0, x_t], dim=-1)
+        x_s0 = torch.cat([x_s0, x_s], dim=-1)
+    return x_t, x_s, x_t0, x_s0
+
+
+class _SeqConv(nn.Module):
+    """gnn.Sequential([HodgeLaguerreConv(K=1) [, gnn.BatchNorm, ReLU, Dropout]]) of the TSP head
+    (lib/Hodge_ST_Model.py:806-817): children module_0 (conv) [, module_1 (BN)]."""
+
+    def __init__(self, fin, fout, with_bn, dropout=0.0):
+        super().__init__()
+        from .Hodge_Cheb_Conv import HodgeLaguerreConv, GraphBatchNorm
+        self.module_0 = HodgeLaguerreConv(fin, fout, K=1)
+        if with_bn:
+            self.module_1 = GraphBatchNorm(fout)
+        self.with_bn, self.p = with_bn, dropout
+
+    def forward(self, x, op, nvalid=None):
+        x = self.module_0(x, op, None)
+        if self.with_bn:
+            x = self.module_1.forward_act(x, 0.0, nvalid)
+            if self.p > 0.0:
+                x = torch.nn.functional.dropout(x, self.p, self.training)
+        return x
+
+
+class HL_HGCNN_TSP_dense_int3_pyr(nn.Module):
+    """Reference lib/Hodge_ST_Model.py:756-852 (per-edge output, readout through |B1^T x_t|/2 :848)."""
+
+    def __init__(self, channels=[2, 2, 2], filters=[64, 128, 256], mlp_channels=[], K=2, node_dim=2, edge_dim=1,
+                 num_classes=1, dropout_ratio=0.0, dropout_ratio_mlp=0.0, keig=20):
+        super().__init__()
+        self.channels, self.filters, self.mlp_channels = channels, filters, mlp_channels
+        self.node_dim, self.edge_dim = node_dim, edge_dim
+        self.initial_channel = self.filters[0]
+        _build_stack(self, K, K, dropout_ratio)
+        mlp_insize = self.filters[-1] * 2
+        if len(self.mlp_channels) == 1:
+            self.mlp = _SeqConv(mlp_insize, self.mlp_channels[0], True, dropout_ratio)
+            mlp_insize = self.mlp_channels[0]
+        self.out = _SeqConv(mlp_insize, num_classes, False)
+
+    def forward(self, data, device="cuda:0"):
+        x_t = data.x_t
+        x_s, edge_mask = data.x_s[:, :1], data.x_s[:, 1:]
+        lv = _Level(data, x_t.shape[0], x_s.shape[0], 1e-6, x_t.device)
+        x_t, x_s = self.HL_init_conv(x_t, lv.op_t, None, x_s, lv.op_s, None, lv.nv)
+        x_t0, x_s0 = x_t, x_s
+        for i, _ in enumerate(self.channels):
+            x_t, x_s, x_t0, x_s0 = _stage(self, i, lv, x_t0, x_s0)
+        x_s = torch.cat([x_s, F_hl.boundary_absdiff(x_t, lv.inc)], dim=-1)
+        if len(self.mlp_channels) == 1:
+            x_s = self.mlp(x_s, lv.op_s, lv.nv[1])
+        s_batch = lv.segments()[1].owner.long()
+        return self.out(x_s, lv.op_s) * edge_mask, s_batch
+
+
+class _AttPool(nn.Module):
+    def _build_head(self, num_classes, dropout_ratio_mlp):
+        mlp_insize = self.filters[-1] * 2
+        for i, mlp_outsize in enumerate(self.mlp_channels):
+            setattr(self, "mlp%d" % i, _MlpBlock(nn.Linear(mlp_insize, mlp_outsize), nn.BatchNorm1d(mlp_outsize),
+                                                 nn.ReLU(), nn.Dropout(dropout_ratio_mlp)))
+            mlp_insize = mlp_outsize
+        self.out = nn.Linear(mlp_insize, num_classes)
+
+    @staticmethod
+    def _positions(datas, lv0, n1, e1, device):
+        """lib/Hodge_ST_Model.py:1027-1036: float cluster ids (column 0 of x_t / x_s) offset by the level-1
+        sizes of the preceding graphs; bucketed once into pooling segments (+inf = edge inside a cluster)."""
+        seg_n, seg_e = lv0.segments()
+        n_ahead = torch.cumsum(torch.as_tensor(datas[1].num_node1, device=device), 0) - torch.as_tensor(datas[1].num_node1, device=device)
+        s_ahead = torch.cumsum(torch.as_tensor(datas[1].num_edge1, device=device), 0) - torch.as_tensor(datas[1].num_edge1, device=device)
+        pos_t = (datas[0].x_t[:, 0] + n_ahead[seg_n.owner.long()]).view(-1, 1)
+        pos_s = (datas[0].x_s[:, 0] + s_ahead[seg_e.owner.long()]).view(-1, 1)
+        return F_hl.Segments.from_index(pos_t, nrows=n1), F_hl.Segments.from_index(pos_s, nrows=e1)
+
+    def _head(self, x_t, x_s, lv):
+        seg_n, seg_e = lv.segments()
+        x = torch.cat((F_hl.segment_mean(x_s, seg_e), F_hl.segment_mean(x_t, seg_n)), -1)
+        for i, _ in enumerate(self.mlp_channels):
+            x = getattr(self, "mlp%d" % i)(x, lv.nv_g)
+        return x
+
+
+class HL_HGCNN_CIFAR10SP_dense_int3_attpool(_AttPool):
+    """Reference lib/Hodge_ST_Model.py:958-1091.  As in the reference, the ReLU gate (normalised by its
+    batch maximum, :1059-1060) only rescales the stage outputs x_t / x_s, which the next stage overwrites;
+    the dense-connection buffers are pooled ungated (:1064-1067)."""
+
+    def __init__(self, channels=[2, 2, 2], filters=[64, 128, 256], mlp_channels=[], K=2, node_dim=5, l=0.5, edge_dim=4,
+                 num_classes=10, dropout_ratio=0.0, dropout_ratio_mlp=0.0, pool_loc=0, keig=10):
+        super().__init__()
+        self.channels, self.filters, self.mlp_channels = channels, filters, mlp_channels
+        self.node_dim, self.edge_dim = node_dim + keig, edge_dim + keig
+        self.initial_channel = self.filters[0]
+        self.pool_loc = pool_loc
+        _build_stack(self, K, 1, dropout_ratio)
+        f = self.filters[pool_loc]
+        setattr(self, f"NEAtt{pool_loc}", NodeEdgeInt(d=f, dv=f, only_att=True, sigma=nn.ReLU(), l=l))
+        self._build_head(num_classes, dropout_ratio_mlp)
+
+    def forward(self, datas, device="cuda:0", if_final_layer=False, if_att=False):
+        d0, d1 = datas[0], datas[1]
+        dev = d0.x_t.device
+        lv = _Level(d0, d0.x_t.shape[0], d0.x_s.shape[0], 1e-6, dev)
+        n1, e1 = d1.x_t.shape[0], d1.x_s.shape[0]
+        seg_pt, seg_ps = self._positions(datas, lv, n1, e1, dev)
+        x_t, x_s = self.HL_init_conv(d0.x_t[:, 1:], lv.op_t, None, d0.x_s[:, 1:], lv.op_s, None, lv.nv)
+        x_t0, x_s0 = x_t, x_s
+        att_t = att_s = None
+        for i, _ in enumerate(self.channels):
+            x_t, x_s, x_t0, x_s0 = _stage(self, i, lv, x_t0, x_s0)
+            if i == self.pool_loc:
+                att_t, att_s = getattr(self, "NEAtt%d" % i)(x_t, x_s, lv.inc, lv.D)
+                att_t = att_t / att_t.max()
+                att_s = att_s / att_s.max()
+                x_t, x_s = x_t * att_t, x_s * att_s
+                x_t0 = F_hl.segment_mean(x_t0, seg_pt)
+                x_s0 = F_hl.segment_mean(x_s0, seg_ps)
+                lv = _Level(d1, n1, e1, 1e-6, dev)
+        x = self._head(x_t, x_s, lv)
+        if if_final_layer:
+            return x, self.out(x)
+        if if_att:
+            return self.out(x), att_t, att_s
+        return self.out(x)
+
+
+class HL_HGCNN_pepfunc_dense_int3_attpool(_AttPool):
+    """Reference main_pepfunc_HL_HGCNN_dense_int3_attpool.py:36-168 (the class the peptides-func script
+    trains): a sigmoid gate on the whole dense-connection buffer after EVERY stage (:131-134); at stage
+    pool_loc the gate multiply is fused into the cluster-mean kernel (:137-143)."""
+
+    def __init__(self, channels=[2, 2, 2, 2], filters=[64, 128, 256, 512], mlp_channels=[], K=2, node_dim=9, edge_dim=3,
+                 num_classes=10, dropout_ratio=0.0, dropout_ratio_mlp=0.0, pool_loc=0, keig=20):
+        super().__init__()
+        self.channels, self.filters, self.mlp_channels = channels, filters, mlp_channels
+        self.node_dim, self.edge_dim = node_dim + keig, edge_dim + keig
+        self.initial_channel = self.filters[0]
+        self.pool_loc = pool_loc
+        self.relu = nn.ReLU()
+        _build_stack(self, K, 1, dropout_ratio)
+        for i, f in enumerate(self.filters):
+            setattr(self, f"NEAtt{i}", NodeEdgeInt(d=self._stage_width[i], dv=f, only_att=True, l=0.5))
+        self._build_head(num_classes, dropout_ratio_mlp)
+
+    def forward(self, datas, device="cuda:0", if_att=False, if_final_layer=False):
+        d0, d1 = datas[0], datas[1]
+        dev = d0.x_t.device
+        lv = _Level(d0, d0.x_t.shape[0], d0.x_s.shape[0], 1e-6, dev)
+        n1, e1 = d1.x_t.shape[0], d1.x_s.shape[0]
+        seg_pt, seg_ps = self._positions(datas, lv, n1, e1, dev)
+        x_t, x_s = self.HL_init_conv(d0.x_t[:, 1:], lv.op_t, None, d0.x_s[:, 1:], lv.op_s, None, lv.nv)
+        x_t0, x_s0 = x_t, x_s
+        last = len(self.channels) - 1
+        for i, _ in enumerate(self.channels):
+            x_t, x_s, x_t0, x_s0 = _stage(self, i, lv, x_t0, x_s0)
+            if i == last and not if_att:
+                break                      # the last gate only rescales buffers nothing reads (:131-134 then :150)
+            att_t, att_s = getattr(self, "NEAtt%d" % i)(x_t0, x_s0, lv.inc, lv.D)
+            if i == self.pool_loc:
+                x_t0 = F_hl.segment_mean(x_t0, seg_pt, att_t)
+                x_s0 = F_hl.segment_mean(x_s0, seg_ps, att_s)
+                lv = _Level(d1, n1, e1, 1e-6, dev)
+            elif i != last:
+                x_t0, x_s0 = x_t0 * att_t, x_s0 * att_s
+        x = self._head(x_t, x_s, lv)
+        if if_att:
+            return self.out(x), att_t, att_s
+        elif if_final_layer:
+            return x, self.out(x)
+        return self.out(x)

@@ -162,11 +162,27 @@ int hl_segment_reduce(const int32_t* rowptr, const int32_t* colidx, int32_t nrow
  * Two-endpoint gather per edge (no atomics):
  *   dst[e,:] = cscale * ( f(src[tail[e],:]) + f(src[head[e],:]) ),  f(v_n) = node_rcp ? (1/node_rcp[n]) * v_n : v_n
  * Replaces: torch.sparse.mm(par.abs().transpose(0,1), x_t)/2  lib/Hodge_Cheb_Conv.py:295 (=:101),
- *           lib/Hodge_ST_Model.py:848; and the adjoint of :294.
+ *           and the adjoint of :294.
  * -------------------------------------------------------------------------------------------- */
 int hl_endpoint_gather(const int32_t* tail, const int32_t* head, int32_t nedges,
                        const float* src, int64_t ld_src, const float* node_rcp,
                        float* dst, int64_t ld_dst, int32_t width, float cscale, hl_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Signed boundary difference per edge, absolute value (no atomics), and its adjoint:
+ *   fwd: dst[e,:]  = cscale * | src[head[e],:] - src[tail[e],:] |
+ *   bwd: dsrc[n,:] = cscale * sum_{e incident to n, ascending e} s(n,e) * sgn(src[head_e]-src[tail_e]) * g[e,:],
+ *        s(n,e) = +1 (n = head of e) / -1 (n = tail of e); sgn(0) = 0 like torch.abs' backward.
+ * Replaces: torch.sparse.mm(par_1.transpose(0,1), x_t).abs()/2   lib/Hodge_ST_Model.py:848 (TSP readout).
+ * inc_rowptr / inc_edge: node -> incident-edge CSR (hl_csr_from_coo with HL_TIE_COLUMN).
+ * -------------------------------------------------------------------------------------------- */
+int hl_boundary_absdiff_fwd(const int32_t* tail, const int32_t* head, int32_t nedges,
+                            const float* src, int64_t ld_src, float* dst, int64_t ld_dst,
+                            int32_t width, float cscale, hl_stream_t stream);
+int hl_boundary_absdiff_bwd(const int32_t* inc_rowptr, const int32_t* inc_edge,
+                            const int32_t* tail, const int32_t* head, int32_t nnodes,
+                            const float* src, int64_t ld_src, const float* g, int64_t ld_g,
+                            float* dsrc, int64_t ld_dsrc, int32_t width, float cscale, hl_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
  * Owner gather (adjoint of hl_segment_reduce w.r.t. src, fused with the gate's adjoint):
