@@ -6,7 +6,8 @@
 One "step" = one training pass (forward + backward + gradient all-reduce + Adam) of the reference's
 ZINC model (HL_HGCNN_zinc_dense_int3_pyr, channels [2,2,2], filters [64,128,256], K=2, fp32) over one
 synthetic ZINC-shaped mini-batch of 1024 graphs PER GPU (BASELINE.json configs[1]; weak scaling).
-Prints ONE JSON line (rank 0).
+Prints ONE JSON line (rank 0).  `--workload peptides|cifar|tsp` runs the other BASELINE.json configs
+(hlhgat_b200/workloads.py) through the same harness.
 """
 import argparse
 import json
@@ -24,10 +25,7 @@ _OUT = sys.stdout
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-MODEL_CTOR = dict(channels=[2, 2, 2], filters=[64, 128, 256], mlp_channels=[], K=2, node_dim=21, edge_dim=3, keig=7)
-BATCH = 1024
 POOL = 4                      # distinct synthetic batches cycled through
-METRIC = "train graphs/sec ZINC-shaped (HL_HGCNN_zinc_dense_int3_pyr, batch 1024/GPU, K=2, fp32)"
 
 
 def peaks():
@@ -96,20 +94,30 @@ def dist_setup(n_gpus):
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle restatement of the reference on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_throughput(steps, warmup, sample_batch):
+def cpu_reference_throughput(wl, steps, warmup, sample_batch):
+    """The oracle restatement of the reference model of workload `wl` (same class name, same ctor arguments,
+    same loss, Adam) on `sample_batch`-graph batches, all host cores."""
     from oracle import hodge_oracle as O
-    from hlhgat_b200.synthetic import make_batch
+    from hlhgat_b200.workloads import focal_loss
     torch.manual_seed(0)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    model = O.HL_HGCNN_zinc_dense_int3_pyr(**MODEL_CTOR).train()
+    model = getattr(O, wl.model)(**wl.ctor).train()
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3)
-    crit = torch.nn.L1Loss()
-    batches = [make_batch("zinc", sample_batch, seed=100 + i) for i in range(2)]
+    batches = [wl.make(sample_batch, 100 + i) for i in range(2)]
+
+    def loss_of(b):
+        if wl.model.endswith("attpool"):
+            out = model(b, if_att=True)[0]
+            y = b[0].y
+            return torch.nn.functional.cross_entropy(out, y) if y.dtype == torch.int64 else focal_loss(out, y)
+        if "TSP" in wl.model:
+            return focal_loss(model(b)[0], b.y.view(-1, 1))
+        return torch.nn.functional.l1_loss(model(b), b.y)
 
     def step(b):
         opt.zero_grad()
-        loss = crit(model(b), b.y)
+        loss = loss_of(b)
         loss.backward()
         opt.step()
         return loss.item()
@@ -126,16 +134,18 @@ def cpu_reference_throughput(steps, warmup, sample_batch):
 def run_reference(args, world, rank):
     if rank != 0:
         return
-    sample = 256
-    gps, ms, cores = cpu_reference_throughput(args.steps, args.warmup, sample)
-    line = {"impl": "reference", "metric": METRIC, "value": gps, "unit": "graphs/s", "n_gpus": args.gpus,
+    from hlhgat_b200.workloads import WORKLOADS
+    wl = WORKLOADS[args.workload]
+    sample = wl.cpu_sample
+    gps, ms, cores = cpu_reference_throughput(wl, args.steps, args.warmup, sample)
+    line = {"impl": "reference", "metric": wl.metric, "value": gps, "unit": "graphs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "zinc_pyr_train_b1024_K2_fp32", "note": "CPU: pure-torch restatement of the "
+            "config": {"workload": wl.label, "note": "CPU: pure-torch restatement of the "
                        "reference (PyG not installable), not PyG itself"},
             "cpu_baseline": {"value": gps, "unit": "graphs/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} training steps on {sample}-graph ZINC-shaped batches "
-                                       f"(a bounded sample of the 1024-graph workload), {cores} torch threads"},
+                             "sample": f"{args.steps} training steps on {sample}-graph batches "
+                                       f"(a bounded sample of the {wl.batch}-graph workload), {cores} torch threads"},
             "e2e": {"value": gps, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=_OUT, flush=True)
 
@@ -156,11 +166,18 @@ def ncu_traffic_bytes():
 # ------------------------------------------------------------------------------------------------
 # roofline leg: the polynomial SpMM kernel on an operator stack larger than L2
 # ------------------------------------------------------------------------------------------------
-def spmm_roofline(dev, batch_dev, reps=16, width=64, iters=20):
-    """Fused L0+L1 launch (HL_EPI_LAGUERRE_FIRST, the K=2 model's forward SpMM) on the bench batch
-    replicated `reps` times block-diagonally so x and T_1 (2 x ~200 MB) exceed the 126 MB L2."""
+ROOFLINE_CASES = {
+    # workload: (block-diagonal replication, feature width): sized so inputs + outputs exceed the 126 MB L2
+    "zinc": (16, 64), "peptides": (40, 64), "cifar": (4, 64), "tsp": (4, 32),
+}
+
+
+def spmm_roofline(dev, batch_dev, workload="zinc", iters=20):
+    """Fused L0+L1 launch (HL_EPI_LAGUERRE_FIRST: T_1 = x - A x, the first SpMM of every conv) on the bench
+    batch replicated `reps` times block-diagonally so that x and T_1 exceed the 126 MB L2."""
     from hlhgat_b200 import functional as F_hl, _native as N
     from hlhgat_b200.simplex import CsrOperator
+    reps, width = ROOFLINE_CASES[workload]
     ops, xs, nnz_tot, rows_tot = [], [], 0, 0
     for ei, ew, r in ((batch_dev.edge_index_t, batch_dev.edge_weight_t, batch_dev.x_t.shape[0]),
                       (batch_dev.edge_index_s, batch_dev.edge_weight_s, batch_dev.x_s.shape[0])):
@@ -185,47 +202,57 @@ def spmm_roofline(dev, batch_dev, reps=16, width=64, iters=20):
     ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
     pk, kind = peaks()
     ach = alg_bytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "poly_spmm_staged_kernel<LAGUERRE_FIRST> (fused L0+L1 launch, cp.async.bulk ring)",
-            "achieved": ach, "peak": pk["hbm_gbs"], "peak_kind": f"{kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
-            "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic_bytes(),
-            "traffic_source": "profiles/r1_spmm_v3_staged_full.txt (ncu --set full of tools/spmm_probe.py, same operator stack)",
-            "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": ms * 1e3,
-            "workload": f"ZINC-shaped B={BATCH}x{reps} block-diagonal, rows {rows_tot}, nnz {nnz_tot}, F={width}; "
-                        "inputs+outputs > L2"}
+    out = {"bound": "hbm", "kernel": "polynomial SpMM, fused L0+L1 launch (poly_spmm_staged_kernel / poly_spmm_kernel, chosen per operator)",
+           "achieved": ach, "peak": pk["hbm_gbs"], "peak_kind": f"{kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+           "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+           "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": ms * 1e3,
+           "workload": f"{workload}-shaped bench batch x{reps} block-diagonal, rows {rows_tot}, nnz {nnz_tot}, F={width}; "
+                       "inputs+outputs > L2"}
+    if workload == "zinc":
+        out["traffic"] = ncu_traffic_bytes()
+        out["traffic_source"] = "profiles/r1_spmm_v3_staged_full.txt (ncu --set full of tools/spmm_probe.py, same operator stack)"
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, world, rank, local):
     import hlhgat_b200
     from hlhgat_b200 import _native as N
-    from hlhgat_b200.lib.Hodge_ST_Model import HL_HGCNN_zinc_dense_int3_pyr
+    from hlhgat_b200.lib import Hodge_ST_Model as M
     from hlhgat_b200.parallel import FlatGradBucket, broadcast_parameters
-    from hlhgat_b200.synthetic import make_batch, batch_to, pin_batch, batch_nbytes, TENSOR_KEYS
-    from hlhgat_b200.simplex import clear_caches
+    from hlhgat_b200.synthetic import batch_to
+    from hlhgat_b200.workloads import WORKLOADS
+    from hlhgat_b200.training import Capacity, pad_batch, pad_levels, padded_nbytes, GraphedTrainStep
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
     hlhgat_b200.build()
+    wl = WORKLOADS[args.workload]
+    batch_size = wl.batch
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     torch.manual_seed(0)
-    model = HL_HGCNN_zinc_dense_int3_pyr(**MODEL_CTOR).to(dev).train()
+    model = getattr(M, wl.model)(**wl.ctor).to(dev).train()
     broadcast_parameters(model)
     bucket = FlatGradBucket(model.parameters())
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3, fused=True, capturable=True)
-    crit = torch.nn.L1Loss()
 
-    from hlhgat_b200.training import Capacity, pad_batch, padded_nbytes, GraphedTrainStep, StaticBatch
-    raw = [make_batch("zinc", BATCH, seed=1000 * rank + i) for i in range(POOL)]
-    cap = Capacity.covering(raw)
+    raw = [wl.make(batch_size, 1000 * rank + i) for i in range(args.pool)]
+    levels = [[b[l] for b in raw] for l in range(wl.levels)] if wl.levels > 1 else [raw]
+    caps = [Capacity.covering(lv) for lv in levels]
     if world > 1:                                        # same capacity on every rank (same graph shapes)
-        t = torch.tensor([cap.nodes, cap.edges, cap.nnz_t, cap.nnz_s], device=dev)
+        t = torch.tensor([[c.nodes, c.edges, c.nnz_t, c.nnz_s] for c in caps], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        cap.nodes, cap.edges, cap.nnz_t, cap.nnz_s = (int(v) for v in t.tolist())
-    host = [pad_batch(b, cap, pin=True) for b in raw]    # pinned host buffers in the reference's batch format
+        for c, row in zip(caps, t.tolist()):
+            c.nodes, c.edges, c.nnz_t, c.nnz_s = (int(v) for v in row)
+    # pinned host buffers in the reference's batch format, padded to the fixed capacity
+    if wl.levels > 1:
+        host = [pad_levels(b, caps, pin=True, deg_eps=wl.deg_eps) for b in raw]
+    else:
+        host = [pad_batch(b, caps[0], pin=True, deg_eps=wl.deg_eps) for b in raw]
     h2d_bytes = padded_nbytes(host[0])
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-    stepper = GraphedTrainStep(model, crit, opt, bucket, host[0], dev, warmup=3)
+    stepper = GraphedTrainStep(model, wl.loss, opt, bucket, host[0], dev, warmup=3, loss_fn=True)
     resident = []
     for b in host:
         stepper.batch.load(b)
@@ -253,11 +280,11 @@ def run_ours(args, world, rank, local):
         return ms
 
     def step_resident(i):                                # inputs already in HBM: D2D into the graph's static buffers
-        stepper.batch.load(resident[i % POOL])
+        stepper.batch.load(resident[i % args.pool])
         stepper.step()
 
     def step_e2e(i):                                     # host buffers in, loss out, every step
-        stepper.batch.load(host[i % POOL], non_blocking=True)
+        stepper.batch.load(host[i % args.pool], non_blocking=True)
         loss = stepper.step()
         loss_host.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -273,33 +300,35 @@ def run_ours(args, world, rank, local):
     launches = stepper.launches_per_step * args.steps
     final_loss = float(loss_host)
 
-    value = BATCH * world * args.steps / (ms * 1e-3)
-    e2e = BATCH * world * args.steps / (ms_e2e * 1e-3)
+    value = batch_size * world * args.steps / (ms * 1e-3)
+    e2e = batch_size * world * args.steps / (ms_e2e * 1e-3)
     if rank != 0:
         return
-    line = {"metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
+    cap_txt = " + ".join(f"{c.nodes} nodes / {c.edges} edges" for c in caps)
+    line = {"metric": wl.metric, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "zinc_pyr_train_b1024_K2_fp32", "graphs_per_gpu": BATCH, "global_batch": BATCH * world,
-                       "parallelism": f"dp{world}", "batch_pool": POOL,
-                       "l2": "no explicit flush: per-step working set (activations saved for backward, ~1 GB) exceeds the 126 MB L2 "
-                             "and consecutive steps use different batches",
+            "config": {"workload": wl.label, "graphs_per_gpu": batch_size, "global_batch": batch_size * world,
+                       "parallelism": f"dp{world}", "batch_pool": args.pool,
+                       "l2": "no explicit flush: per-step working set (activations saved for backward, ~1 GB or more) exceeds the "
+                             "126 MB L2 and consecutive steps use different batches",
                        "execution": "whole step (CSR bucketing + forward + backward) replayed as one CUDA graph on batches padded "
-                                    f"to a fixed capacity ({cap.nodes} nodes / {cap.edges} edges, ~2% ghost rows), then all-reduce + fused Adam graph",
+                                    f"to a fixed capacity ({cap_txt}, ~2% ghost rows), then all-reduce + fused Adam graph",
                        "gemm": "dense Theta/MLP transforms + data/weight gradients: hand-written tcgen05 3xTF32 kernels (fp32-accurate); "
-                               "cuBLAS fp32 only for the 10-column edge input of the first conv"},
+                               "cuBLAS fp32 only for shapes with N % 16 != 0 or unaligned rows (first-layer inputs)"},
             "e2e": {"value": e2e, "unit": "graphs/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "gpu_launches_note": "libhlhgat kernels inside the replayed graph x steps (cuBLAS/ATen launches not counted)",
             "final_loss": final_loss, "clocks": clocks}
     try:
-        line["roofline"] = spmm_roofline(dev, batch_to(raw[0], dev))
+        b0 = raw[0][0] if wl.levels > 1 else raw[0]
+        line["roofline"] = spmm_roofline(dev, batch_to(b0, dev), args.workload)
     except Exception as exc:  # pragma: no cover
         line["roofline"] = {"error": repr(exc)}
     if world == 1 and not args.no_cpu_baseline:
-        gps, ms_cpu, cores = cpu_reference_throughput(3, 1, 256)
+        gps, ms_cpu, cores = cpu_reference_throughput(wl, 3, 1, wl.cpu_sample)
         line["cpu_baseline"] = {"value": gps, "unit": "graphs/s", "cores": cores, "kind": "port",
-                                "sample": "3 training steps (1 warm-up) on 256-graph ZINC-shaped batches, same model, "
+                                "sample": f"3 training steps (1 warm-up) on {wl.cpu_sample}-graph batches of the same shape, same model, "
                                           f"{cores} torch threads; pure-torch restatement of the reference, not PyG"}
     print(json.dumps(line), file=_OUT, flush=True)
 
@@ -322,6 +351,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="zinc", choices=["zinc", "peptides", "cifar", "tsp"],
+                    help="BASELINE.json config: zinc = configs[1] (the headline metric, default); the others are the "
+                         "peptides-func / CIFAR10-superpixel / TSP-shaped configs")
+    ap.add_argument("--pool", type=int, default=POOL, help="distinct synthetic batches cycled through")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     world, rank, local = dist_setup(args.gpus)

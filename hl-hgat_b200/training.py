@@ -35,8 +35,10 @@ class Capacity(SimpleNamespace):
                    graphs=max(b.num_graphs for b in batches))
 
 
-def pad_batch(b, cap, pin=False):
-    """Host-side padding of a collated batch to `cap` (data preparation, like the collate itself)."""
+def pad_batch(b, cap, pin=False, deg_eps=0.0):
+    """Host-side padding of a collated batch to `cap` (data preparation, like the collate itself).
+    `deg_eps`: the constant the model adds to the node degree (0 for the ZINC model, 1e-6 elsewhere);
+    a target `y` with one row per edge (TSP) is padded like the edge features."""
     n, e = b.x_t.shape[0], b.x_s.shape[0]
     g = b.num_graphs
     assert n < cap.nodes and e < cap.edges and g == cap.graphs
@@ -57,7 +59,8 @@ def pad_batch(b, cap, pin=False):
         return out
 
     p = SimpleNamespace(num_graphs=g)
-    p.x_t, p.x_s, p.y = rows(b.x_t, cap.nodes), rows(b.x_s, cap.edges), b.y.clone()
+    p.x_t, p.x_s = rows(b.x_t, cap.nodes), rows(b.x_s, cap.edges)
+    p.y = rows(b.y, cap.edges) if (b.y.dim() and b.y.shape[0] == e and e != g) else b.y.clone()
     p.edge_index = cols(b.edge_index, cap.edges, n, cap.nodes - n)          # ghost edges: self-pairs on ghost nodes
     p.edge_index_t = cols(b.edge_index_t, cap.nnz_t, n, cap.nodes - n)      # ghost entries: (g, g) with weight 0
     p.edge_index_s = cols(b.edge_index_s, cap.nnz_s, e, cap.edges - e)
@@ -65,6 +68,7 @@ def pad_batch(b, cap, pin=False):
     p.num_node1 = torch.cat([b.num_node1, torch.tensor([cap.nodes - n])])
     p.num_edge1 = torch.cat([b.num_edge1, torch.tensor([cap.edges - e])])
     deg = torch.zeros(cap.nodes).index_add_(0, b.edge_index.reshape(-1), torch.ones(2 * e))
+    deg = deg + deg_eps
     deg[n:] = 1.0                                                # ghost nodes: finite 1/D
     p.D = deg
     p.n_valid_nodes = torch.tensor([n], dtype=torch.int32)
@@ -77,23 +81,49 @@ def pad_batch(b, cap, pin=False):
 
 
 def padded_nbytes(p):
+    if isinstance(p, (list, tuple)):
+        return sum(padded_nbytes(q) for q in p)
     return sum(getattr(p, k).numel() * getattr(p, k).element_size() for k in _PAD_KEYS)
 
 
+def pad_levels(datas, caps, pin=False, deg_eps=1e-6):
+    """Two-level batches of the attention-pooling models: every level is padded on its own.  Ghost
+    rows of level 0 carry cluster id 0 inside the ghost graph, i.e. they pool into the first ghost row
+    of level 1 (all-zero features either way)."""
+    return [pad_batch(d, c, pin, deg_eps) for d, c in zip(datas, caps)]
+
+
 class StaticBatch:
-    """Device buffers of one capacity; `load` overwrites them in place (H2D or D2D copies)."""
+    """Device buffers of one capacity; `load` overwrites them in place (H2D or D2D copies).  A list of
+    padded levels gives a list-like StaticBatch (`batch[0]`, `batch[1]`)."""
 
     def __init__(self, proto, device):
+        self.levels = None
+        if isinstance(proto, (list, tuple)):
+            self.levels = [StaticBatch(p, device) for p in proto]
+            return
         self.num_graphs = proto.num_graphs
         for k in _PAD_KEYS:
             setattr(self, k, torch.empty_like(getattr(proto, k), device=device))
         self.load(proto)
 
+    def __getitem__(self, i):
+        return self.levels[i]
+
+    def __len__(self):
+        return len(self.levels)
+
     def load(self, p, non_blocking=True):
+        if self.levels is not None:
+            for lv, q in zip(self.levels, p):
+                lv.load(q, non_blocking)
+            return
         for k in _PAD_KEYS:
             getattr(self, k).copy_(getattr(p, k), non_blocking=non_blocking)
 
     def clone_resident(self):
+        if self.levels is not None:
+            return [lv.clone_resident() for lv in self.levels]
         out = SimpleNamespace(num_graphs=self.num_graphs)
         for k in _PAD_KEYS:
             setattr(out, k, getattr(self, k).clone())
@@ -102,10 +132,13 @@ class StaticBatch:
 
 class GraphedTrainStep:
     """forward + loss + backward captured once; replayed per step on the batch currently loaded in
-    `self.batch`.  `optimizer` must be capturable (e.g. Adam(fused=True, capturable=True))."""
+    `self.batch`.  `optimizer` must be capturable (e.g. Adam(fused=True, capturable=True)).
+    `criterion` is either a loss module applied to `(model(batch)[:num_graphs], batch.y)` (graph-level
+    targets) or, with `loss_fn=True`, a callable `criterion(model, batch) -> scalar loss`."""
 
-    def __init__(self, model, criterion, optimizer, bucket, proto_batch, device, warmup=3):
+    def __init__(self, model, criterion, optimizer, bucket, proto_batch, device, warmup=3, loss_fn=False):
         self.model, self.criterion, self.optimizer, self.bucket = model, criterion, optimizer, bucket
+        self.loss_fn = loss_fn
         self.device = device
         self.batch = StaticBatch(proto_batch, device)
         self.loss = torch.zeros((), device=device)
@@ -133,9 +166,12 @@ class GraphedTrainStep:
     def _fwd_bwd(self):
         clear_caches()                     # the static COO buffers change content between replays
         self.bucket.zero()
-        g = self.batch.num_graphs
-        pred = self.model(self.batch, device=self.device)
-        loss = self.criterion(pred[:g], self.batch.y)
+        if self.loss_fn:
+            loss = self.criterion(self.model, self.batch)
+        else:
+            g = self.batch.num_graphs
+            pred = self.model(self.batch, device=self.device)
+            loss = self.criterion(pred[:g], self.batch.y)
         loss.backward()
         self.loss.copy_(loss.detach())
 

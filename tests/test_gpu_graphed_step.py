@@ -79,3 +79,70 @@ def test_graphed_step_matches_eager_training():
         # into +-lr steps, so only parameters with a real gradient are comparable
         if n.endswith(".weight"):
             assert float((a - r).norm()) < 5e-3 * float(r.norm()), n
+
+
+# ---------------------------------------------------------------------------------------------
+# the other workloads (two-level attpool batches, per-edge TSP targets) through the same machinery
+# ---------------------------------------------------------------------------------------------
+def _small(wl_name):
+    from hlhgat_b200.workloads import WORKLOADS
+    import copy as _c
+    wl = _c.copy(WORKLOADS[wl_name])
+    ctor = dict(wl.ctor)
+    ctor.update(channels=[1, 1, 1], filters=[32, 32, 64])
+    if wl_name != "tsp":
+        ctor.update(mlp_channels=[48])
+    wl.ctor = ctor
+    return wl
+
+
+@pytest.mark.parametrize("name,nb", [("peptides", 6), ("cifar", 4), ("tsp", 2)])
+def test_padded_equals_unpadded_and_graph_equals_eager_other_workloads(name, nb):
+    from hlhgat_b200.lib import Hodge_ST_Model as M
+    from hlhgat_b200.training import pad_levels
+    from types import SimpleNamespace
+    torch.manual_seed(0)
+    wl = _small(name)
+    if name == "tsp":
+        from hlhgat_b200.synthetic import make_tsp_batch
+        raws = []
+        for s in (1, 2):
+            b = make_tsp_batch(nb, seed=s, n=60 + 10 * s, k=8)
+            b.y = b.y.float()
+            raws.append(b)
+    else:
+        raws = [wl.make(nb, s) for s in (1, 2)]
+
+    def dev_of(b):
+        return SimpleNamespace(**{k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in vars(b).items()})
+
+    if wl.levels > 1:
+        caps = [Capacity.covering([r[l] for r in raws], slack=0.1) for l in range(2)]
+        host = [pad_levels(r, caps, pin=True, deg_eps=wl.deg_eps) for r in raws]
+        plain = [[dev_of(l) for l in r] for r in raws]
+    else:
+        caps = [Capacity.covering(raws, slack=0.1)]
+        host = [pad_batch(r, caps[0], pin=True, deg_eps=wl.deg_eps) for r in raws]
+        plain = [dev_of(r) for r in raws]
+    model = getattr(M, wl.model)(**wl.ctor).to(DEV).train()
+    ref = copy.deepcopy(model)
+    # (1) padded == unpadded, eager
+    loss_ref = wl.loss(ref, plain[0])
+    g_ref = torch.autograd.grad(loss_ref, list(ref.parameters()), allow_unused=True)
+    sb = StaticBatch(host[0], DEV)
+    loss_p = wl.loss(model, sb)
+    assert abs(float(loss_p) - float(loss_ref)) < 1e-4 * max(1.0, abs(float(loss_ref))), (float(loss_p), float(loss_ref))
+    g = torch.autograd.grad(loss_p, list(model.parameters()), allow_unused=True)
+    for (n, _), a, r in zip(model.named_parameters(), g, g_ref):
+        assert (a is None) == (r is None), n
+        if a is not None:
+            assert float((a - r).norm()) < 2e-3 * float(r.norm()) + 1e-6 * r.numel() ** 0.5 * max(1.0, float(loss_ref)), n
+    # (2) graph replay == eager on the padded batch
+    m_graph = copy.deepcopy(ref)
+    bucket = FlatGradBucket(m_graph.parameters())
+    opt = torch.optim.SGD(m_graph.parameters(), lr=0.0)
+    stepper = GraphedTrainStep(m_graph, wl.loss, opt, bucket, host[0], DEV, warmup=2, loss_fn=True)
+    stepper.batch.load(host[1])
+    lg = float(stepper.step())
+    le = float(wl.loss(copy.deepcopy(ref), StaticBatch(host[1], DEV)))
+    assert abs(lg - le) < 1e-4 * max(1.0, abs(le)), (lg, le)
