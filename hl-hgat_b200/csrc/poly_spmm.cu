@@ -183,10 +183,10 @@ static int launch_poly_spmm(const hl_spmm_problem* probs, int n, int32_t width, 
     const int rc = launch_poly_spmm_staged(probs, n, width, epi, s0, s1, s2, s3, stream);
     if (rc != 1) return rc;                                  // 1 = not applicable, fall through
   }
-  // two vectors per lane whenever the row is wide enough to keep >= 4 lanes busy: halves the
+  // two vectors per lane whenever the row is wide enough to keep >= 8 lanes busy: halves the
   // per-row index/address instruction overhead and every lane still reads full 128-byte lines
   const int chunks = (width + V - 1) / V;
-  const int CH = chunks >= 8 ? 2 : 1;
+  const int CH = chunks >= 16 ? 2 : 1;                       // (at 8 chunks two vectors per lane would touch half lines)
   int G = 1;
   while (G * CH < chunks && G < 32) G <<= 1;
   const int tile_w = G * V * CH;
