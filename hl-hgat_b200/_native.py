@@ -69,9 +69,9 @@ _SIGNATURES = {
     "hl_colsum_workspace": (_sz, [_i32, _i32]),
     "hl_colsum": (C.c_int, [_vp, _i64, _i32, _i32, _vp, C.c_int, _vp, _sz, _vp]),
     "hl_bn_workspace": (_sz, [_i32, _i32]),
-    "hl_bn_act_fwd": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _vp, _i64, _vp, _vp, _vp, _vp, _f32, _vp, _sz, _vp]),
+    "hl_bn_act_fwd": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _vp, _i64, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _sz, _vp]),
     "hl_bn_act_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32,
-                                _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+                                _vp, _i64, _vp, _vp, C.c_int, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -72,9 +72,11 @@ __device__ __forceinline__ void warp_sum2(double& a, double& b) {
 __global__ void bn_stats_final_kernel(const double* __restrict__ partial, int nblk, const float* __restrict__ x,
                                       int32_t nrows_cap, const int32_t* __restrict__ nvalid, int32_t width,
                                       float* __restrict__ stats, float* __restrict__ running_mean,
-                                      float* __restrict__ running_var, float momentum) {
+                                      float* __restrict__ running_var, float momentum,
+                                      long long* __restrict__ batches_tracked) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  if (batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *batches_tracked += 1;   // nn.BatchNorm1d.num_batches_tracked
   if (c >= width) return;
   const int32_t nrows = nvalid ? min(__ldg(nvalid), nrows_cap) : nrows_cap;
   double a = 0.0, b = 0.0;
@@ -192,7 +194,8 @@ bn_bwd_partial_kernel(const float* __restrict__ x, int64_t ld_x, const float* __
 
 // sums[0:F] = sum dz (= dbeta), sums[F:2F] = sum dz*xhat (= dgamma); one warp per column
 __global__ void bn_bwd_final_kernel(const double* __restrict__ partial, int nblk, int32_t width,
-                                    float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                    float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                    int accumulate) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (c >= width) return;
@@ -205,8 +208,8 @@ __global__ void bn_bwd_final_kernel(const double* __restrict__ partial, int nblk
   if (lane == 0) {
     sums[c] = (float)a;
     sums[width + c] = (float)b;
-    if (dbeta) dbeta[c] = (float)a;
-    if (dgamma) dgamma[c] = (float)b;
+    if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)a : (float)a;
+    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)b : (float)b;
   }
 }
 
@@ -264,6 +267,7 @@ extern "C" int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_
                              const float* gamma, const float* beta, float eps, float slope,
                              float* y, int64_t ld_y, float* stats, const int32_t* nvalid,
                              float* running_mean, float* running_var, float momentum,
+                             int64_t* num_batches_tracked,
                              void* workspace, size_t workspace_bytes, hl_stream_t stream) {
   using namespace hl;
   if (nrows < 1 || width < 1 || !x || !y || !stats) return HL_ERR_INVALID;
@@ -279,7 +283,8 @@ extern "C" int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_
   else bn_stats_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
   HL_LAUNCH_CHECK("bn_stats_partial_kernel");
   bn_stats_final_kernel<<<(width * 32 + 255) / 256, 256, 0, st>>>(partial, nblk, x, nrows, nvalid, width, stats,
-                                                                    running_mean, running_mean ? running_var : nullptr, momentum);
+                                                                    running_mean, running_mean ? running_var : nullptr, momentum,
+                                                                    reinterpret_cast<long long*>(num_batches_tracked));
   HL_LAUNCH_CHECK("bn_stats_final_kernel");
   const int g = ew_grid((int64_t)nrows * (width / V));
   if (V == 4) bn_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
@@ -292,8 +297,8 @@ extern "C" int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_
 extern "C" int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64_t ld_y,
                              const float* dy, int64_t ld_dy, int32_t nrows, int32_t width,
                              const float* gamma, const float* stats, float eps, float slope,
-                             float* dx, int64_t ld_dx, float* dgamma, float* dbeta, const int32_t* nvalid,
-                             void* workspace, size_t workspace_bytes, hl_stream_t stream) {
+                             float* dx, int64_t ld_dx, float* dgamma, float* dbeta, int accumulate_param_grads,
+                             const int32_t* nvalid, void* workspace, size_t workspace_bytes, hl_stream_t stream) {
   using namespace hl;
   if (nrows < 1 || width < 1 || !x || !y || !dy || !dx || !stats) return HL_ERR_INVALID;
   if (!workspace || workspace_bytes < hl_bn_workspace(nrows, width)) return HL_ERR_WORKSPACE;
@@ -311,7 +316,7 @@ extern "C" int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64
   else if (V == 2) bn_bwd_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
   else bn_bwd_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
   HL_LAUNCH_CHECK("bn_bwd_partial_kernel");
-  bn_bwd_final_kernel<<<(width * 32 + 255) / 256, 256, 0, st>>>(partial, nblk, width, sums, dgamma, dbeta);
+  bn_bwd_final_kernel<<<(width * 32 + 255) / 256, 256, 0, st>>>(partial, nblk, width, sums, dgamma, dbeta, accumulate_param_grads);
   HL_LAUNCH_CHECK("bn_bwd_final_kernel");
   const int g = ew_grid((int64_t)nrows * (width / V));
   if (V == 4) bn_bwd_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx);

@@ -8,8 +8,9 @@
 //
 // Structure (one CTA = one 128 x BN output tile, BN = N <= 256):
 //   warp 0      TMA producer: A tile (128x32 fp32, 128B swizzle) + pre-split B_hi / B_lo tiles per k-block
-//   warps 2-5   converters: split the landed A tile in place into hi (in place) and lo (second buffer) --
-//               an elementwise pass, so it is oblivious to the swizzled layout -- then
+//   warps 2-5   converters: write lo = x - trunc_tf32(x) of the landed A tile into a second buffer (an elementwise
+//               pass, so it is oblivious to the swizzled layout); the landed fp32 tile itself serves as hi, because
+//               kind::tf32 reads only the sign, exponent and top 10 mantissa bits of each 32-bit element -- then
 //               fence.proxy.async and signal the MMA warp; after the main loop the same warps run the
 //               epilogue (tcgen05.ld 32x32b -> registers -> bias / accumulate -> 128-bit global stores)
 //   warp 1      one elected lane issues 3 x 4 tcgen05.mma (M=128, N=BN, K=8) per k-block into TMEM and
@@ -232,8 +233,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
         h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
         l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
-        a[idx] = h;
-        alo[idx] = l;
+        alo[idx] = l;                                               // hi stays implicit: kind::tf32 ignores the low 13 mantissa bits
       }
       if (MODE == 1) {
         float4* b = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + 2 * a_bytes);
@@ -246,7 +246,6 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
           h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
           l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
-          b[idx] = h;
           blo[idx] = l;
         }
       }
@@ -415,6 +414,18 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
   int stages = (int)((200 * 1024) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 2) return 1;
+  // a ring deeper than the k-loop only costs shared memory; and when the grid is between one and two waves
+  // (ZINC: 189-205 row tiles on 148 SMs) a ring that fits twice per SM lets all CTAs be resident at once, so the
+  // fixed per-CTA cost (TMEM allocation, descriptor fetch, pipeline fill, epilogue) of the "second wave" overlaps
+  const int num_kb = (Ktot + kGmBK - 1) / kGmBK;
+  if (stages > num_kb) stages = num_kb < 2 ? 2 : num_kb;
+  static int co_resident = -1;
+  if (co_resident < 0) { const char* e = getenv("HL_GEMM_CORESIDENT"); co_resident = e ? atoi(e) : 1; }
+  const int64_t ctas = (int64_t)((M + kGmBM - 1) / kGmBM) * ntiles;
+  if (co_resident && ctas > 148 && ctas <= 2 * 148) {
+    const int s2 = (int)((108 * 1024) / stage_bytes);
+    if (s2 >= 2 && stages > s2) stages = s2;
+  }
   const size_t smem = stages * stage_bytes + (3 * stages + 2) * sizeof(uint64_t) + 1024;
 
   CUtensorMap ma, mbh, mbl, ma2;
@@ -437,15 +448,34 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
   return HL_OK;
 }
 
-__global__ void gm_split_reduce_kernel(const float* __restrict__ partial, int32_t splits, int64_t split_stride, int32_t fo,
-                                       int32_t fi, float* __restrict__ dw, int64_t ld_dw, int accumulate) {
+// dw (=|+=) sum over the row splits: 8 lanes per output element (k = lane, lane + 8, ...), fixed shuffle tree
+__global__ void __launch_bounds__(256)
+gm_split_reduce_kernel(const float* __restrict__ partial, int32_t splits, int64_t split_stride, int32_t fo,
+                       int32_t fi, float* __restrict__ dw, int64_t ld_dw, int accumulate) {
   const int64_t n = (int64_t)fo * fi;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const int sub = threadIdx.x & 7;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < ((n + 31) & ~(int64_t)31);
+       i += ((int64_t)gridDim.x * blockDim.x) >> 3) {
     float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += partial[(int64_t)k * split_stride + i];
-    const int64_t o = i / fi, c = i - o * fi;
-    float* p = dw + o * ld_dw + c;
-    *p = accumulate ? *p + s : s;
+    if (i < n) {
+      int k = sub;
+      for (; k + 24 < splits; k += 32) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(partial + (int64_t)(k + 8 * u) * split_stride + i);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s += v[u];
+      }
+      for (; k < splits; k += 8) s += __ldg(partial + (int64_t)k * split_stride + i);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (sub == 0 && i < n) {
+      const int64_t o = i / fi, c = i - o * fi;
+      float* p = dw + o * ld_dw + c;
+      *p = accumulate ? *p + s : s;
+    }
   }
 }
 
@@ -503,7 +533,7 @@ extern "C" int hl_wgrad_tf32x3(const float* g, int64_t ld_g, const float* x, int
   gemm_tf32x3_kernel<1><<<grid, kGmThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
   HL_LAUNCH_CHECK("gemm_tf32x3_kernel<wgrad>");
   const int64_t n = (int64_t)fo * fi;
-  gm_split_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, as_stream(stream)>>>(P.C, splits, P.split_stride, fo, fi, dw, ld_dw,
+  gm_split_reduce_kernel<<<(int)((n * 8 + 255) / 256), 256, 0, as_stream(stream)>>>(P.C, splits, P.split_stride, fo, fi, dw, ld_dw,
                                                                                accumulate);
   HL_LAUNCH_CHECK("gm_split_reduce_kernel");
   return HL_OK;

@@ -56,6 +56,37 @@ def set_dense_backend(name):
     """"tcgen05" (default): 3xTF32 tensor-core GEMM from libhlhgat; "cublas": torch.mm (fp32 SIMT SGEMM)."""
     _GEMM_MODE["tensor"] = name == "tcgen05"
 
+_BACKWARD_MODE = {"accumulate": False}
+
+
+class accumulate_into_grads:
+    """Fused gradient accumulation.  Wrap `loss.backward()` in this context (training.GraphedTrainStep does):
+    inside it the kernels that produce weight / bias / BatchNorm-affine gradients ADD them straight into an
+    existing dense fp32 `param.grad` (e.g. the views of parallel.FlatGradBucket) and hand autograd `None`
+    for those inputs -- the same values autograd's own `grad.add_(new)` would leave there, without one extra
+    elementwise launch per parameter.  Outside the context (and under `torch.autograd.grad`) gradients are
+    returned as usual."""
+
+    def __enter__(self):
+        self.prev = _BACKWARD_MODE["accumulate"]
+        _BACKWARD_MODE["accumulate"] = True
+        return self
+
+    def __exit__(self, *a):
+        _BACKWARD_MODE["accumulate"] = self.prev
+
+
+def _grad_target(p):
+    """`p.grad` if the producing kernel may accumulate into it directly, else None."""
+    if not _BACKWARD_MODE["accumulate"] or not isinstance(p, torch.nn.Parameter):
+        return None
+    g = p.grad
+    if g is None or not g.is_cuda or g.dtype != torch.float32 or g.shape != p.shape or g.stride(-1) != 1:
+        return None
+    if g.dim() == 2 and g.stride(0) < g.shape[1]:
+        return None
+    return g
+
 
 def dense(a, w, bias=None, out=None, accumulate=False, transpose_w=False):
     """out (=|+=) a @ w.T (+ bias)   [transpose_w: a @ w].  fp32-accurate tcgen05 GEMM (3xTF32 split) when the
@@ -104,8 +135,9 @@ def dense2(a1, w1, a2, w2, bias=None, out=None, accumulate=False):
     if ok:
         k1p = (k1 + 31) // 32 * 32
         kt = k1p + k2
-        hi = torch.zeros((n_out, kt), dtype=torch.float32, device=a1.device)
-        lo = torch.zeros((n_out, kt), dtype=torch.float32, device=a1.device)
+        alloc = torch.empty if k1p == k1 else torch.zeros          # pad columns k1..k1p of the packed weights must be 0
+        hi = alloc((n_out, kt), dtype=torch.float32, device=a1.device)
+        lo = alloc((n_out, kt), dtype=torch.float32, device=a1.device)
         st = N.stream_ptr()
         N.check(L.hl_tf32_split(w1.data_ptr(), w1.stride(0), n_out, k1, 0, hi.data_ptr(), lo.data_ptr(), kt, st), "hl_tf32_split")
         N.check(L.hl_tf32_split(w2.data_ptr(), w2.stride(0), n_out, k2, 0, hi[:, k1p:].data_ptr(), lo[:, k1p:].data_ptr(), kt, st),
@@ -123,8 +155,8 @@ def dense2(a1, w1, a2, w2, bias=None, out=None, accumulate=False):
     return dense(a2, w2, None, out=out, accumulate=True)
 
 
-def wgrad(g, x, out=None):
-    """dW[Fo,Fi] = g[R,Fo]^T x[R,Fi] (deterministic split-row reduction); `out` may be a column slice."""
+def wgrad(g, x, out=None, accumulate=False):
+    """dW[Fo,Fi] (=|+=) g[R,Fo]^T x[R,Fi] (deterministic split-row reduction); `out` may be a column slice."""
     L = N.lib()
     g, ldg = N.row_major(g)
     x, ldx = N.row_major(x)
@@ -132,10 +164,12 @@ def wgrad(g, x, out=None):
     fi = x.shape[1]
     if out is None:
         out = torch.empty((fo, fi), dtype=torch.float32, device=g.device)
+        accumulate = False
+    acc = 1 if accumulate else 0
     if _GEMM_MODE["tensor"]:
         nb = L.hl_wgrad_tf32x3_workspace(R, fo, fi)
         ws = torch.empty(nb, dtype=torch.uint8, device=g.device)
-        rc = L.hl_wgrad_tf32x3(g.data_ptr(), ldg, x.data_ptr(), ldx, R, fo, fi, out.data_ptr(), out.stride(0), 0,
+        rc = L.hl_wgrad_tf32x3(g.data_ptr(), ldg, x.data_ptr(), ldx, R, fo, fi, out.data_ptr(), out.stride(0), acc,
                                ws.data_ptr(), nb, N.stream_ptr())
         if rc == 0:
             return out
@@ -143,19 +177,22 @@ def wgrad(g, x, out=None):
             N.check(rc, "hl_wgrad_tf32x3")
     nb = L.hl_wgrad_workspace(R, fo, fi)
     ws = torch.empty(nb, dtype=torch.uint8, device=g.device)
-    N.check(L.hl_wgrad(g.data_ptr(), ldg, x.data_ptr(), ldx, R, fo, fi, out.data_ptr(), out.stride(0), 0,
+    N.check(L.hl_wgrad(g.data_ptr(), ldg, x.data_ptr(), ldx, R, fo, fi, out.data_ptr(), out.stride(0), acc,
                        ws.data_ptr(), nb, N.stream_ptr()), "hl_wgrad")
     return out
 
 
-def colsum(g):
+def colsum(g, out=None):
+    """out[f] (=|+=) sum_r g[r,f]; accumulates when `out` is given."""
     L = N.lib()
     g, ldg = N.row_major(g)
     R, f = g.shape
-    out = torch.empty(f, dtype=torch.float32, device=g.device)
+    acc = 0 if out is None else 1
+    if out is None:
+        out = torch.empty(f, dtype=torch.float32, device=g.device)
     nb = L.hl_colsum_workspace(R, f)
     ws = torch.empty(nb, dtype=torch.uint8, device=g.device)
-    N.check(L.hl_colsum(g.data_ptr(), ldg, R, f, out.data_ptr(), 0, ws.data_ptr(), nb, N.stream_ptr()), "hl_colsum")
+    N.check(L.hl_colsum(g.data_ptr(), ldg, R, f, out.data_ptr(), acc, ws.data_ptr(), nb, N.stream_ptr()), "hl_colsum")
     return out
 
 
@@ -175,6 +212,7 @@ class _Linear(torch.autograd.Function):
             y = dense2(xa, weight[:, :d], xb, weight[:, d:], bias)
         ctx.save_for_backward(xa, xb, weight)
         ctx.has_bias = bias is not None
+        ctx.params = (weight, bias)                 # the Parameter objects (for fused gradient accumulation)
         return y
 
     @staticmethod
@@ -188,12 +226,18 @@ class _Linear(torch.autograd.Function):
         if xb is not None and ctx.needs_input_grad[1]:
             gb = dense(g, weight[:, d:], transpose_w=True)
         if ctx.needs_input_grad[2]:
-            gw = torch.empty_like(weight)
-            wgrad(g, xa, gw[:, :d])
+            tgt = _grad_target(ctx.params[0])
+            gw = torch.empty_like(weight) if tgt is None else tgt
+            wgrad(g, xa, gw[:, :d], accumulate=tgt is not None)
             if xb is not None:
-                wgrad(g, xb, gw[:, d:])
+                wgrad(g, xb, gw[:, d:], accumulate=tgt is not None)
+            if tgt is not None:
+                gw = None
         if ctx.has_bias and ctx.needs_input_grad[3]:
-            gbias = colsum(g)
+            tgt = _grad_target(ctx.params[1])
+            gbias = colsum(g, out=tgt)
+            if tgt is not None:
+                gbias = None
         return ga, gb, gw, gbias
 
 
@@ -223,6 +267,7 @@ class _PolyConv(torch.autograd.Function):
                 else:
                     dense(t[k - 1].view(-1, inner), weights[k], None, out=out, accumulate=True)
         ctx.op, ctx.family, ctx.inner, ctx.has_bias = op, family, inner, bias is not None
+        ctx.params = (bias, weights)
         ctx.save_for_backward(x, t, *weights)
         return out
 
@@ -245,10 +290,17 @@ class _PolyConv(torch.autograd.Function):
         for k in range(K):
             if ctx.needs_input_grad[5 + k]:
                 src = x if k == 0 else t[k - 1]
-                gws.append(wgrad(g, src.view(-1, inner)))
+                tgt = _grad_target(ctx.params[1][k])
+                gw = wgrad(g, src.view(-1, inner), out=tgt, accumulate=tgt is not None)
+                gws.append(None if tgt is not None else gw)
             else:
                 gws.append(None)
-        gb = colsum(g) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
+        gb = None
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            tgt = _grad_target(ctx.params[0])
+            gb = colsum(g, out=tgt)
+            if tgt is not None:
+                gb = None
         return (gx, gb, None, None, None, *gws)
 
 
@@ -490,7 +542,7 @@ def segment_mean(src, seg, scale=None):
 # ---------------------------------------------------------------------------------------------
 class _BnAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, slope, nvalid, running_mean, running_var, momentum):
+    def forward(ctx, x, gamma, beta, eps, slope, nvalid, running_mean, running_var, momentum, counter=None):
         N.require_cuda_f32(x, gamma, beta)
         L = N.lib()
         x, ldx = N.row_major(x)
@@ -501,8 +553,10 @@ class _BnAct(torch.autograd.Function):
         ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
         N.check(L.hl_bn_act_fwd(x.data_ptr(), ldx, R, F, N.ptr(gamma), N.ptr(beta), eps, slope,
                                 y.data_ptr(), y.stride(0), stats.data_ptr(), N.ptr(nvalid), N.ptr(running_mean),
-                                N.ptr(running_var), float(momentum), ws.data_ptr(), nb, N.stream_ptr()), "hl_bn_act_fwd")
+                                N.ptr(running_var), float(momentum), N.ptr(counter), ws.data_ptr(), nb, N.stream_ptr()),
+                "hl_bn_act_fwd")
         ctx.eps, ctx.slope, ctx.nvalid = eps, slope, nvalid
+        ctx.params = (gamma, beta)
         ctx.save_for_backward(x, y, gamma, stats)
         ctx.mark_non_differentiable(stats)
         return y, stats
@@ -514,19 +568,25 @@ class _BnAct(torch.autograd.Function):
         R, F = x.shape
         dy, lddy = N.row_major(dy)
         dx = torch.empty((R, F), dtype=torch.float32, device=x.device)
-        dgamma = torch.empty(F, dtype=torch.float32, device=x.device)
-        dbeta = torch.empty(F, dtype=torch.float32, device=x.device)
+        tg, tb = _grad_target(ctx.params[0]), _grad_target(ctx.params[1])
+        fused = tg is not None and tb is not None
+        dgamma = tg if fused else torch.empty(F, dtype=torch.float32, device=x.device)
+        dbeta = tb if fused else torch.empty(F, dtype=torch.float32, device=x.device)
         nb = L.hl_bn_workspace(R, F)
         ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
         N.check(L.hl_bn_act_bwd(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), dy.data_ptr(), lddy, R, F,
                                 N.ptr(gamma), stats.data_ptr(), ctx.eps, ctx.slope, dx.data_ptr(), dx.stride(0),
-                                dgamma.data_ptr(), dbeta.data_ptr(), N.ptr(ctx.nvalid), ws.data_ptr(), nb,
+                                dgamma.data_ptr(), dbeta.data_ptr(), 1 if fused else 0, N.ptr(ctx.nvalid), ws.data_ptr(), nb,
                                 N.stream_ptr()), "hl_bn_act_bwd")
-        return dx, dgamma, dbeta, None, None, None, None, None, None
+        if fused:
+            dgamma = dbeta = None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None
 
 
-def bn_act_train(x, gamma, beta, eps=1e-5, slope=0.0, nvalid=None, running_mean=None, running_var=None, momentum=0.1):
+def bn_act_train(x, gamma, beta, eps=1e-5, slope=0.0, nvalid=None, running_mean=None, running_var=None, momentum=0.1,
+                 counter=None):
     """Training-mode BatchNorm1d over rows + (leaky) ReLU; returns (y, stats[2F] = mean | biased var).
     `nvalid`: optional device int32 scalar -- rows beyond it are padding (excluded, written as zeros).
-    running_mean / running_var (optional) are updated in the same launch, like nn.BatchNorm1d."""
-    return _BnAct.apply(x, gamma, beta, float(eps), float(slope), nvalid, running_mean, running_var, momentum)
+    running_mean / running_var (optional) are updated in the same launch, like nn.BatchNorm1d; `counter`
+    (optional int64 scalar: num_batches_tracked) is incremented there too."""
+    return _BnAct.apply(x, gamma, beta, float(eps), float(slope), nvalid, running_mean, running_var, momentum, counter)

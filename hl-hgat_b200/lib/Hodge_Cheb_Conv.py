@@ -245,10 +245,14 @@ def _bn_relu(bn, x, slope=0.0, nvalid=None):
         return torch.nn.functional.leaky_relu(y, slope) if slope != 1.0 else y
     track = bn.track_running_stats and bn.training
     if track:
-        with torch.no_grad():
-            bn.num_batches_tracked += 1
-        m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-        y, _ = F_hl.bn_act_train(x, bn.weight, bn.bias, bn.eps, slope, nvalid, bn.running_mean, bn.running_var, m)
+        counter = bn.num_batches_tracked
+        if bn.momentum is None:               # cumulative average: the factor depends on the counter (host read)
+            with torch.no_grad():
+                bn.num_batches_tracked += 1
+            m, counter = 1.0 / float(bn.num_batches_tracked), None
+        else:
+            m = bn.momentum                   # the counter is incremented inside the statistics kernel
+        y, _ = F_hl.bn_act_train(x, bn.weight, bn.bias, bn.eps, slope, nvalid, bn.running_mean, bn.running_var, m, counter)
     else:
         y, _ = F_hl.bn_act_train(x, bn.weight, bn.bias, bn.eps, slope, nvalid)
     return y

@@ -14,6 +14,7 @@ from types import SimpleNamespace
 
 import torch
 
+from .functional import accumulate_into_grads
 from .simplex import clear_caches
 
 _PAD_KEYS = ("x_t", "x_s", "y", "edge_index", "edge_index_t", "edge_index_s", "edge_weight_t", "edge_weight_s",
@@ -172,7 +173,8 @@ class GraphedTrainStep:
             g = self.batch.num_graphs
             pred = self.model(self.batch, device=self.device)
             loss = self.criterion(pred[:g], self.batch.y)
-        loss.backward()
+        with accumulate_into_grads():              # weight gradients land in the flat bucket directly
+            loss.backward()
         self.loss.copy_(loss.detach())
 
     def step(self):

@@ -227,12 +227,14 @@ int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_t width,
                   const float* gamma, const float* beta, float eps, float slope,
                   float* y, int64_t ld_y, float* stats, const int32_t* nvalid /* device, nullable */,
                   float* running_mean /* nullable */, float* running_var, float momentum,
+                  int64_t* num_batches_tracked /* device, nullable: incremented by one in the same launch */,
                   void* workspace, size_t workspace_bytes, hl_stream_t stream);
 int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64_t ld_y,
                   const float* dy, int64_t ld_dy, int32_t nrows, int32_t width,
                   const float* gamma, const float* stats, float eps, float slope,
-                  float* dx, int64_t ld_dx, float* dgamma, float* dbeta, const int32_t* nvalid,
-                  void* workspace, size_t workspace_bytes, hl_stream_t stream);
+                  float* dx, int64_t ld_dx, float* dgamma, float* dbeta,
+                  int accumulate_param_grads /* dgamma / dbeta: 0 = overwrite, 1 = += (fused gradient accumulation) */,
+                  const int32_t* nvalid, void* workspace, size_t workspace_bytes, hl_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
  * fp32-accurate dense transform on the tcgen05 tensor cores (3xTF32 split, fp32 TMEM accumulator):
