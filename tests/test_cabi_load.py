@@ -61,3 +61,30 @@ def test_state_dict_contract_matches_reference_names():
     assert [tuple(l.weight.shape) for l in conv.lins] == [(7, 3)] * 4 and conv.bias.abs().sum() == 0
     with pytest.raises(AssertionError):
         H.HodgeLaguerreConv(3, 7, 0)
+
+
+def test_pairdata_collate_matches_reference_batch():
+    """hlhgat_b200.lib.Hodge_Dataset.PairData + collate reproduce the batch PyG's DataLoader built from the
+    reference's PairData.__inc__ (golden: tests/golden/zinc_model.pt), and the list-of-levels form."""
+    import torch
+    from conftest import load_golden
+    from oracle import hodge_oracle as O
+    from hlhgat_b200.lib.Hodge_Dataset import PairData, collate
+    z = load_golden("zinc_model.pt")
+    b = z["batch"]
+    graphs, off_n, off_e = [], 0, 0
+    for g in z["raw"]:
+        c = O.build_simplex_graph(g["ei_dir"], g["n"])
+        e = c.edge_index.shape[1]
+        d = PairData(x_s=b["x_s"][off_e:off_e + e], edge_index_s=c.edge_index_s, edge_weight_s=c.edge_weight_s,
+                     x_t=b["x_t"][off_n:off_n + g["n"]], edge_index_t=c.edge_index_t, edge_weight_t=c.edge_weight_t,
+                     y=torch.zeros(1))
+        d.num_node1, d.num_edge1, d.num_nodes, d.edge_index = g["n"], e, g["n"], c.edge_index
+        graphs.append(d)
+        off_n, off_e = off_n + g["n"], off_e + e
+    bb = collate(graphs)
+    for k in ("x_t", "x_s", "edge_index", "edge_index_t", "edge_index_s", "edge_weight_t", "edge_weight_s", "num_node1", "num_edge1"):
+        assert torch.equal(getattr(bb, k), b[k]), k
+    assert bb.num_graphs == len(graphs) and bb.num_nodes == off_n and bb.ptr[-1] == off_n
+    levels = collate([[g, g] for g in graphs])
+    assert isinstance(levels, list) and len(levels) == 2 and torch.equal(levels[1].edge_index_s, b["edge_index_s"])

@@ -101,3 +101,14 @@ def test_model_runs_on_constructed_batch_like_host_built_batch():
     (c,) = F_hl.poly_basis_fwd(N.HL_LAGUERRE, 4, [sb.op_s], [x], 64)
     assert torch.allclose(a, c, rtol=1e-5, atol=1e-6)
     assert torch.equal(host_op.fwd[1], sb.op_s.fwd[1]) and torch.equal(host_op.fwd[0], sb.op_s.fwd[0])
+
+
+def test_dataset_process_mirror_on_golden_graphs():
+    """lib.Hodge_Dataset.simplex_batch_from_graphs = Dataset.process (lib/Hodge_Dataset.py:447-477) for a list of
+    raw graphs with LOCAL node ids; same golden vectors as above."""
+    from hlhgat_b200.lib.Hodge_Dataset import simplex_batch_from_graphs
+    graphs = load_golden("construct.pt")
+    sb = simplex_batch_from_graphs([g["ei_dir"] for g in graphs], [g["n"] for g in graphs], device=DEV,
+                                   edge_attrs=[torch.arange(g["ei_dir"].shape[1]) % 3 + 1 for g in graphs])
+    _check_against(graphs, sb)
+    assert torch.equal(sb.edge_attr.cpu(), torch.cat([g["edge_attr"] for g in graphs]))
