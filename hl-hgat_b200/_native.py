@@ -68,6 +68,7 @@ _SIGNATURES = {
     "hl_wgrad": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, C.c_int, _vp, _sz, _vp]),
     "hl_colsum_workspace": (_sz, [_i32, _i32]),
     "hl_colsum": (C.c_int, [_vp, _i64, _i32, _i32, _vp, C.c_int, _vp, _sz, _vp]),
+    "hl_greedy_matching": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hl_bn_workspace": (_sz, [_i32, _i32]),
     "hl_bn_act_fwd": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _vp, _i64, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _sz, _vp]),
     "hl_bn_act_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32,

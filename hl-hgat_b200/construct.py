@@ -54,6 +54,27 @@ def build_simplex_batch(src, dst, node_counts, edge_attr=None, max_steps=None):
     n_edges = int(n_edges_dev)                                  # the one host sync of the construction
     tail, head = tail[:n_edges].contiguous(), head[:n_edges].contiguous()
 
+    return _finish(tail, head, node_counts, node_ptr64, n_nodes, attr_out, max_steps, lexicographic=True)
+
+
+def simplex_batch_from_edges(tail, head, node_counts, max_steps=None):
+    """Operators of a batch whose UNIQUE undirected edges are already known: `tail` < `head` (int32, global node
+    ids), in ANY order -- the order is kept (rows of L1 follow it), as the coarse graphs of MLGC need, whose edge
+    list is in first-appearance order (lib/Hodge_Dataset.py:262-275)."""
+    dev = tail.device
+    node_counts = node_counts.to(dev, torch.int64)
+    node_ptr64 = torch.zeros(node_counts.numel() + 1, dtype=torch.int64, device=dev)
+    node_ptr64[1:] = torch.cumsum(node_counts, 0)
+    return _finish(tail.to(torch.int32).contiguous(), head.to(torch.int32).contiguous(), node_counts, node_ptr64,
+                   int(node_ptr64[-1]), None, max_steps, lexicographic=False)
+
+
+def _finish(tail, head, node_counts, node_ptr64, n_nodes, attr_out, max_steps, lexicographic):
+    L = N.lib()
+    dev = tail.device
+    st = N.stream_ptr()
+    G = int(node_counts.numel())
+    n_edges = int(tail.numel())
     # 2. node -> incident edges (ascending edge id)
     ar = torch.arange(n_edges, dtype=torch.int64, device=dev)
     rows = torch.cat([tail, head]).long()
@@ -90,6 +111,13 @@ def build_simplex_batch(src, dst, node_counts, edge_attr=None, max_steps=None):
                                 inc_edge.data_ptr(), node_graph.data_ptr(), lam.data_ptr(),
                                 r0.data_ptr(), c0.data_ptr(), v0.data_ptr(), r1.data_ptr(), c1.data_ptr(), v1.data_ptr(),
                                 st), "hl_laplacian_fill")
+
+    if not lexicographic and nnz0:
+        # hl_laplacian_fill emits L0 neighbours in incident-edge order, which is ascending only for a
+        # lexicographic edge list; restore the row-major ascending order of dense_to_sparse
+        rows0 = torch.repeat_interleave(torch.arange(n_nodes, device=dev), (r0[1:] - r0[:-1]).long(), output_size=nnz0)
+        perm = torch.argsort(rows0 * n_nodes + c0.long())
+        c0, v0 = c0[perm].contiguous(), v0[perm].contiguous()
 
     b = SimplexBatch()
     b.num_graphs, b.num_nodes, b.num_edges = G, n_nodes, n_edges

@@ -10,10 +10,11 @@ from types import SimpleNamespace
 
 import torch
 
+from ..coarsen import mlgc_batch  # noqa: F401  (MLGC / MLGC_weighted :241-353 for a whole mini-batch, on the GPU)
 from ..construct import build_simplex_batch
 from .Hodge_Cheb_Conv import adj2par1  # noqa: F401  (same name / signature as lib/Hodge_Dataset.py:169)
 
-__all__ = ["PairData", "collate", "adj2par1", "simplex_batch_from_graphs"]
+__all__ = ["PairData", "collate", "adj2par1", "simplex_batch_from_graphs", "mlgc_batch"]
 
 
 class PairData(SimpleNamespace):

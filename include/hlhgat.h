@@ -237,6 +237,18 @@ int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64_t ld_y,
                   const int32_t* nvalid, void* workspace, size_t workspace_bytes, hl_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Greedy heavy-edge matching for multi-level graph coarsening, one warp per graph of the mini-batch.
+ * Nodes are visited in id order; an unmatched node u pairs with its unmatched neighbour of largest edge_weight
+ * (NULL = all ones; ties: first in ascending incident-edge order); cluster[u] = cluster[partner] = u.
+ * Replaces: torch_cluster.graclus_cluster in MLGC / MLGC_weighted (lib/Hodge_Dataset.py:254-255, :309-311) --
+ * the library routine is randomised; this is the deterministic variant the CPU oracle pins.
+ * node_ptr[G+1]: node range of every graph; inc_rowptr/inc_edge: node -> incident-edge CSR; tail/head per edge.
+ * -------------------------------------------------------------------------------------------- */
+int hl_greedy_matching(const int32_t* node_ptr, int32_t n_graphs, const int32_t* inc_rowptr, const int32_t* inc_edge,
+                       const int32_t* tail, const int32_t* head, const float* edge_weight /* nullable */,
+                       int32_t* cluster /* out [N] */, hl_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
  * fp32-accurate dense transform on the tcgen05 tensor cores (3xTF32 split, fp32 TMEM accumulator):
  *   hl_gemm_tf32x3 : C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) , or C += ... when accumulate != 0
  * A row-major [M,K] (pitch lda), B = the layer weight [N,K] pre-split by hl_tf32_split into
