@@ -14,7 +14,7 @@ from ..coarsen import mlgc_batch  # noqa: F401  (MLGC / MLGC_weighted :241-353 f
 from ..construct import build_simplex_batch
 from .Hodge_Cheb_Conv import adj2par1  # noqa: F401  (same name / signature as lib/Hodge_Dataset.py:169)
 
-__all__ = ["PairData", "collate", "adj2par1", "simplex_batch_from_graphs", "mlgc_batch"]
+__all__ = ["PairData", "collate", "adj2par1", "simplex_batch_from_graphs", "mlgc_batch", "two_level_batch_from_graphs"]
 
 
 class PairData(SimpleNamespace):
@@ -98,3 +98,28 @@ def simplex_batch_from_graphs(edge_indices, num_nodes, device="cuda:0", edge_att
     dst = torch.cat([ei[1] + o for ei, o in zip(edge_indices, offs)])
     attr = None if edge_attrs is None else torch.cat(list(edge_attrs)).to(device)
     return build_simplex_batch(src.to(device), dst.to(device), counts, edge_attr=attr)
+
+
+def _as_level(sb, x_t, x_s, y=None):
+    """A `SimplexBatch` in the attribute layout the model classes read (the reference's collated PairData batch),
+    with the device-side CSR / incidence tables attached so that nothing is re-bucketed."""
+    d = PairData(x_t=x_t, x_s=x_s, edge_index=sb.edge_index, y=y)
+    d.edge_index_t, d.edge_weight_t = sb.coo("t")
+    d.edge_index_s, d.edge_weight_s = sb.coo("s")
+    d.num_node1, d.num_edge1 = sb.num_node1, sb.num_edge1
+    d.num_nodes, d.num_graphs = sb.num_nodes, sb.num_graphs
+    d.op_t, d.op_s, d.incidence = sb.op_t, sb.op_s, sb.incidence
+    return d
+
+
+def two_level_batch_from_graphs(edge_indices, num_nodes, x_t, x_s, y=None, device="cuda:0", edge_weight=None):
+    """The `[fine batch, coarse batch]` pair the attention-pooling models consume, built on the GPU from raw graphs:
+    `Dataset.get` (lib/Hodge_Dataset.py:829-870) = construction + MLGC + cluster ids prepended as column 0 of the
+    fine features (:867-868) + list collation.  `x_t` [sum N, F_t] / `x_s` [sum E, F_s] are the fine node / edge
+    features (edges in the lexicographic i<j order of every graph); `edge_weight` (per fine edge) selects
+    MLGC_weighted's heavy-edge matching."""
+    sb0 = simplex_batch_from_graphs(edge_indices, num_nodes, device=device)
+    sb1, c_node, c_edge = mlgc_batch(sb0, edge_weight)
+    lv0 = _as_level(sb0, torch.cat([c_node, x_t.to(device)], -1), torch.cat([c_edge, x_s.to(device)], -1), y)
+    lv1 = _as_level(sb1, torch.ones(sb1.num_nodes, 1, device=device), torch.ones(sb1.num_edges, 1, device=device))
+    return [lv0, lv1]

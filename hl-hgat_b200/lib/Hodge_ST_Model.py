@@ -98,9 +98,10 @@ class _Level:
 
     def __init__(self, d, n, e, eps, device):
         self.n, self.e = n, e
-        self.op_t = operator_for(d.edge_index_t.to(device), d.edge_weight_t.to(device), n)
-        self.op_s = operator_for(d.edge_index_s.to(device), d.edge_weight_s.to(device), e)
-        self.inc = incidence_for(d.edge_index.to(device), n)
+        # batches built on the GPU (lib.Hodge_Dataset.two_level_batch_from_graphs) carry their CSR / incidence tables
+        self.op_t = getattr(d, "op_t", None) or operator_for(d.edge_index_t.to(device), d.edge_weight_t.to(device), n)
+        self.op_s = getattr(d, "op_s", None) or operator_for(d.edge_index_s.to(device), d.edge_weight_s.to(device), e)
+        self.inc = getattr(d, "incidence", None) or incidence_for(d.edge_index.to(device), n)
         D = getattr(d, "D", None)
         self.D = (self.inc.degree() + eps) if D is None else D.to(device)   # degree(edge_index.view(-1), n) + 1e-6
         self.nv = (getattr(d, "n_valid_nodes", None), getattr(d, "n_valid_edges", None))

@@ -98,3 +98,29 @@ def test_weighted_matching_vs_graclus_stand_in():
         off += n
     got = greedy_matching(_fine(eis, ns), torch.cat(ws))
     assert torch.equal(got.cpu().long(), torch.cat(want))
+
+
+def test_attpool_model_on_gpu_built_two_level_batch_equals_host_built():
+    """raw graphs -> GPU construction + GPU MLGC -> model == the same model on the host-built two-level batch."""
+    from types import SimpleNamespace
+    from hlhgat_b200.lib import Hodge_ST_Model as M
+    from hlhgat_b200.lib.Hodge_Dataset import two_level_batch_from_graphs
+    from hlhgat_b200.synthetic import make_multilevel_batch
+    host = make_multilevel_batch("cifar", 5, seed=4, node_dim=8, edge_dim=6)
+    lv0 = host[0]
+    ns = lv0.num_node1.tolist()
+    es = lv0.num_edge1.tolist()
+    eis, n_off, e_off = [], 0, 0
+    for n, e in zip(ns, es):
+        eis.append(lv0.edge_index[:, e_off:e_off + e] - n_off)
+        n_off, e_off = n_off + n, e_off + e
+    datas = two_level_batch_from_graphs(eis, ns, lv0.x_t[:, 1:], lv0.x_s[:, 1:], device=DEV)
+    assert torch.equal(datas[0].x_t[:, 0].cpu(), lv0.x_t[:, 0]) and torch.equal(datas[0].x_s[:, 0].cpu(), lv0.x_s[:, 0])
+    assert torch.equal(datas[1].edge_index.cpu(), host[1].edge_index)
+    torch.manual_seed(0)
+    ctor = dict(channels=[1, 1, 1], filters=[32, 32, 64], mlp_channels=[32], K=3, node_dim=4, edge_dim=2, keig=4, pool_loc=1, num_classes=3)
+    model = M.HL_HGCNN_pepfunc_dense_int3_attpool(**ctor).to(DEV).train()
+    dev_host = [SimpleNamespace(**{k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in vars(d).items()}) for d in host]
+    a = model(datas, device=DEV)
+    b = model(dev_host, device=DEV)
+    assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), float((a - b).abs().max())
