@@ -229,6 +229,9 @@ def run_ours(args, world, rank, local):
     hlhgat_b200.build()
     wl = WORKLOADS[args.workload]
     batch_size = wl.batch
+    factored = args.factored_l1 == "on" or (args.factored_l1 == "auto" and wl.long_rows)
+    from hlhgat_b200 import functional as F_hl
+    F_hl.enable_factored_hodge1(factored)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     torch.manual_seed(0)
@@ -314,6 +317,8 @@ def run_ours(args, world, rank, local):
                              "126 MB L2 and consecutive steps use different batches",
                        "execution": "whole step (CSR bucketing + forward + backward) replayed as one CUDA graph on batches padded "
                                     f"to a fixed capacity ({cap_txt}, ~2% ghost rows), then all-reduce + fused Adam graph",
+                       "edge_operator": ("L1 applied in factored form diag(2/lambda) B1^T B1 (opt-in, fp32-rounding-equal to the CSR path)"
+                                         if factored else "L1 applied from its CSR (bit-exact summation order of the reference)"),
                        "gemm": "dense Theta/MLP transforms + data/weight gradients: hand-written tcgen05 3xTF32 kernels (fp32-accurate); "
                                "cuBLAS fp32 only for shapes with N % 16 != 0 or unaligned rows (first-layer inputs)"},
             "e2e": {"value": e2e, "unit": "graphs/s", "ms_per_step": ms_e2e / args.steps,
@@ -355,6 +360,9 @@ def main():
                     help="BASELINE.json config: zinc = configs[1] (the headline metric, default); the others are the "
                          "peptides-func / CIFAR10-superpixel / TSP-shaped configs")
     ap.add_argument("--pool", type=int, default=POOL, help="distinct synthetic batches cycled through")
+    ap.add_argument("--factored-l1", default="auto", choices=["auto", "on", "off"],
+                    help="apply the edge Laplacian as diag(2/lambda) B1^T B1 instead of its CSR; auto = only for the long-row "
+                         "workloads (cifar, tsp); the ZINC headline always uses the CSR SpMM")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     world, rank, local = dist_setup(args.gpus)

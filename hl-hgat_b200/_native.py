@@ -33,6 +33,11 @@ class ConvSide(C.Structure):
                 ("x", _vp), ("ld_x", _i64), ("t", _vp), ("ld_t", _i64), ("t_stride", _i64), ("g0", _vp), ("ld_g0", _i64)]
 
 
+class Hodge1Operator(C.Structure):
+    _fields_ = [("inc_rowptr", _vp), ("inc_edge", _vp), ("tail", _vp), ("head", _vp), ("edge_scale", _vp),
+                ("n_nodes", _i32), ("n_edges", _i32)]
+
+
 _SIGNATURES = {
     "hl_version": (C.c_int, []),
     "hl_status_string": (C.c_char_p, [C.c_int]),
@@ -68,6 +73,8 @@ _SIGNATURES = {
     "hl_wgrad": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, C.c_int, _vp, _sz, _vp]),
     "hl_colsum_workspace": (_sz, [_i32, _i32]),
     "hl_colsum": (C.c_int, [_vp, _i64, _i32, _i32, _vp, C.c_int, _vp, _sz, _vp]),
+    "hl_poly_basis_hodge1_fwd": (C.c_int, [C.c_int, C.c_int, C.POINTER(Hodge1Operator), _vp, _i64, _vp, _i64, _i64, _vp, _i32, _vp]),
+    "hl_poly_basis_hodge1_bwd": (C.c_int, [C.c_int, C.c_int, C.POINTER(Hodge1Operator), _vp, _i64, _vp, _i64, _i64, _vp, _i32, _vp]),
     "hl_greedy_matching": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hl_bn_workspace": (_sz, [_i32, _i32]),
     "hl_bn_act_fwd": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _vp, _i64, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _sz, _vp]),

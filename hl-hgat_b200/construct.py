@@ -6,7 +6,7 @@ segment kernels over the concatenated directed edge list of all graphs; nothing 
 import torch
 
 from . import _native as N
-from .simplex import CsrOperator, Incidence, csr_from_coo
+from .simplex import CsrOperator, Hodge1Factor, Incidence, csr_from_coo
 
 
 def _ws(nbytes, dev):
@@ -128,6 +128,8 @@ def _finish(tail, head, node_counts, node_ptr64, n_nodes, attr_out, max_steps, l
     b.lambda_max, b.lambda_last_change = lam, change
     b.op_t = CsrOperator.from_csr(r0, c0, v0, n_nodes)
     b.op_s = CsrOperator.from_csr(r1, c1, v1, n_edges)
+    if n_edges:                         # the constructor knows that op_s = diag(2/lambda) B1^T B1: keep the factored form too
+        b.op_s.factored = Hodge1Factor(inc, 2.0 / lam[node_graph[tail.long()].long()])
     b.num_node1 = node_counts
     b.num_edge1 = torch.bincount(node_graph[tail.long()].long(), minlength=G) if n_edges else torch.zeros_like(node_counts)
     b.node_graph = node_graph

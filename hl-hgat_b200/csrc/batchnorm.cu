@@ -60,13 +60,29 @@ bn_stats_partial_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows
   }
 }
 
-// one warp per column: lanes stride over the row blocks, fixed-order shuffle tree
-__device__ __forceinline__ void warp_sum2(double& a, double& b) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, off);
-    b += __shfl_xor_sync(0xffffffffu, b, off);
-  }
+// Column sums of the per-row-block partials.  A 256-thread block owns 8 columns: thread (ks, cl) adds the row
+// blocks ks, ks + 32, ... of column c0 + cl (64-byte coalesced rows of the partial array), then the 32 slices are
+// combined in ascending order through shared memory -- a fixed order, so results are reproducible.  (One warp per
+// column walking all row blocks was latency-bound on long batches: 26 us for the 1800 row blocks of a TSP batch.)
+constexpr int kBnFinalCols = 8;
+__device__ __forceinline__ bool bn_column_sums(const double* __restrict__ partial, int nblk, int32_t width,
+                                               double& a, double& b, int& c) {
+  __shared__ double sh[2][32][kBnFinalCols];
+  const int cl = threadIdx.x & (kBnFinalCols - 1), ks = threadIdx.x / kBnFinalCols;
+  c = blockIdx.x * kBnFinalCols + cl;
+  a = 0.0; b = 0.0;
+  if (c < width)
+    for (int k = ks; k < nblk; k += 32) {
+      a += partial[((int64_t)k * 2 + 0) * width + c];
+      b += partial[((int64_t)k * 2 + 1) * width + c];
+    }
+  sh[0][ks][cl] = a;
+  sh[1][ks][cl] = b;
+  __syncthreads();
+  if (ks != 0 || c >= width) return false;
+  a = 0.0; b = 0.0;
+  for (int j = 0; j < 32; ++j) { a += sh[0][j][cl]; b += sh[1][j][cl]; }
+  return true;
 }
 
 __global__ void bn_stats_final_kernel(const double* __restrict__ partial, int nblk, const float* __restrict__ x,
@@ -74,18 +90,11 @@ __global__ void bn_stats_final_kernel(const double* __restrict__ partial, int nb
                                       float* __restrict__ stats, float* __restrict__ running_mean,
                                       float* __restrict__ running_var, float momentum,
                                       long long* __restrict__ batches_tracked) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
   if (batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *batches_tracked += 1;   // nn.BatchNorm1d.num_batches_tracked
-  if (c >= width) return;
   const int32_t nrows = nvalid ? min(__ldg(nvalid), nrows_cap) : nrows_cap;
-  double a = 0.0, b = 0.0;
-  for (int k = lane; k < nblk; k += 32) {
-    a += partial[((int64_t)k * 2 + 0) * width + c];
-    b += partial[((int64_t)k * 2 + 1) * width + c];
-  }
-  warp_sum2(a, b);
-  if (lane == 0) {
+  double a, b;
+  int c;
+  if (bn_column_sums(partial, nblk, width, a, b, c)) {
     if (nrows > 0) {
       const double n = (double)nrows, m = a / n;
       const float mean = (float)((double)__ldg(x + c) + m);
@@ -196,16 +205,9 @@ bn_bwd_partial_kernel(const float* __restrict__ x, int64_t ld_x, const float* __
 __global__ void bn_bwd_final_kernel(const double* __restrict__ partial, int nblk, int32_t width,
                                     float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                     int accumulate) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (c >= width) return;
-  double a = 0.0, b = 0.0;
-  for (int k = lane; k < nblk; k += 32) {
-    a += partial[((int64_t)k * 2 + 0) * width + c];
-    b += partial[((int64_t)k * 2 + 1) * width + c];
-  }
-  warp_sum2(a, b);
-  if (lane == 0) {
+  double a, b;
+  int c;
+  if (bn_column_sums(partial, nblk, width, a, b, c)) {
     sums[c] = (float)a;
     sums[width + c] = (float)b;
     if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)a : (float)a;
@@ -282,7 +284,7 @@ extern "C" int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_
   else if (V == 2) bn_stats_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
   else bn_stats_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
   HL_LAUNCH_CHECK("bn_stats_partial_kernel");
-  bn_stats_final_kernel<<<(width * 32 + 255) / 256, 256, 0, st>>>(partial, nblk, x, nrows, nvalid, width, stats,
+  bn_stats_final_kernel<<<(width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st>>>(partial, nblk, x, nrows, nvalid, width, stats,
                                                                     running_mean, running_mean ? running_var : nullptr, momentum,
                                                                     reinterpret_cast<long long*>(num_batches_tracked));
   HL_LAUNCH_CHECK("bn_stats_final_kernel");
@@ -316,7 +318,7 @@ extern "C" int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64
   else if (V == 2) bn_bwd_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
   else bn_bwd_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
   HL_LAUNCH_CHECK("bn_bwd_partial_kernel");
-  bn_bwd_final_kernel<<<(width * 32 + 255) / 256, 256, 0, st>>>(partial, nblk, width, sums, dgamma, dbeta, accumulate_param_grads);
+  bn_bwd_final_kernel<<<(width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st>>>(partial, nblk, width, sums, dgamma, dbeta, accumulate_param_grads);
   HL_LAUNCH_CHECK("bn_bwd_final_kernel");
   const int g = ew_grid((int64_t)nrows * (width / V));
   if (V == 4) bn_bwd_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx);

@@ -9,7 +9,7 @@ import math
 import torch
 
 from . import _native as N
-from .simplex import CsrOperator, Incidence, csr_from_coo
+from .simplex import CsrOperator, Hodge1Factor, Incidence, csr_from_coo  # noqa: F401
 
 _FAMILY = {"laguerre": N.HL_LAGUERRE, "cheb": N.HL_CHEB}
 
@@ -25,28 +25,68 @@ def _side(csr, nrows, x=None, ld_x=0, t=None, ld_t=0, t_stride=0, g0=None, ld_g0
     return s
 
 
+_FACTORED = {"enabled": False}
+
+
+def enable_factored_hodge1(flag=True):
+    """Opt in to the factored application L1 x = diag(s) B1^T (B1 x) for operators that carry a `Hodge1Factor`
+    (operators built by construct.build_simplex_batch, or attached by the model classes from the batch's boundary
+    matrix): 4 row gathers per edge instead of one per nonzero of L1.  Off by default -- the CSR path reproduces the
+    reference's summation order bit for bit, the factored one only to fp32 rounding (~1e-7)."""
+    _FACTORED["enabled"] = bool(flag)
+
+
+def factored_hodge1_enabled():
+    return _FACTORED["enabled"]
+
+
+def _use_factored(op):
+    return _FACTORED["enabled"] and getattr(op, "factored", None) is not None
+
+
+def _hodge1_struct(op):
+    f = op.factored
+    inc = f.incidence
+    h = N.Hodge1Operator()
+    h.inc_rowptr, h.inc_edge, h.tail, h.head = inc.rowptr.data_ptr(), inc.edge.data_ptr(), inc.tail.data_ptr(), inc.head.data_ptr()
+    h.edge_scale, h.n_nodes, h.n_edges = f.edge_scale.data_ptr(), inc.num_nodes, inc.num_edges
+    return h
+
+
 def poly_basis_fwd(family, K, ops, xs, width):
     """T_1..T_{K-1} for several operators in K-1 shared launches.  Returns stacked [K-1,R,width]."""
     L = N.lib()
-    sides = (N.ConvSide * len(ops))()
-    outs = []
+    csr = [i for i, op in enumerate(ops) if not _use_factored(op)]
+    sides = (N.ConvSide * max(len(csr), 1))()
+    outs = [None] * len(ops)
     for i, (op, x) in enumerate(zip(ops, xs)):
         x2, ldx = N.row_major(x)
         t = torch.empty((max(K - 1, 0), op.nrows, width), dtype=torch.float32, device=x.device)
-        outs.append(t)
-        sides[i] = _side(op.fwd, op.nrows, x=x2, ld_x=ldx, t=t, ld_t=width, t_stride=op.nrows * width)
-    if K > 1:
-        N.check(L.hl_poly_basis_fwd(family, K, sides, len(ops), width, N.stream_ptr()), "hl_poly_basis_fwd")
+        outs[i] = t
+        if i in csr:
+            sides[csr.index(i)] = _side(op.fwd, op.nrows, x=x2, ld_x=ldx, t=t, ld_t=width, t_stride=op.nrows * width)
+        elif K > 1:
+            tmp = torch.empty((op.factored.incidence.num_nodes, width), dtype=torch.float32, device=x.device)
+            N.check(L.hl_poly_basis_hodge1_fwd(family, K, _hodge1_struct(op), x2.data_ptr(), ldx, t.data_ptr(), width,
+                                               op.nrows * width, tmp.data_ptr(), width, N.stream_ptr()), "hl_poly_basis_hodge1_fwd")
+    if K > 1 and csr:
+        N.check(L.hl_poly_basis_fwd(family, K, sides, len(csr), width, N.stream_ptr()), "hl_poly_basis_fwd")
     return outs
 
 
 def poly_basis_bwd(family, K, ops, g0s, gts, width):
     L = N.lib()
-    sides = (N.ConvSide * len(ops))()
+    csr = [i for i, op in enumerate(ops) if not _use_factored(op)]
+    sides = (N.ConvSide * max(len(csr), 1))()
     for i, (op, g0, gt) in enumerate(zip(ops, g0s, gts)):
-        sides[i] = _side(op.bwd, op.nrows, t=gt, ld_t=width, t_stride=op.nrows * width, g0=g0, ld_g0=width)
-    if K > 1:
-        N.check(L.hl_poly_basis_bwd(family, K, sides, len(ops), width, N.stream_ptr()), "hl_poly_basis_bwd")
+        if i in csr:
+            sides[csr.index(i)] = _side(op.bwd, op.nrows, t=gt, ld_t=width, t_stride=op.nrows * width, g0=g0, ld_g0=width)
+        elif K > 1:
+            tmp = torch.empty((op.factored.incidence.num_nodes, width), dtype=torch.float32, device=g0.device)
+            N.check(L.hl_poly_basis_hodge1_bwd(family, K, _hodge1_struct(op), g0.data_ptr(), width, gt.data_ptr(), width,
+                                               op.nrows * width, tmp.data_ptr(), width, N.stream_ptr()), "hl_poly_basis_hodge1_bwd")
+    if K > 1 and csr:
+        N.check(L.hl_poly_basis_bwd(family, K, sides, len(csr), width, N.stream_ptr()), "hl_poly_basis_bwd")
 
 
 _GEMM_MODE = {"tensor": True}

@@ -5,7 +5,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as F_hl
-from ..simplex import incidence_for, operator_for
+from ..simplex import Hodge1Factor, incidence_for, operator_for
 from .Hodge_Cheb_Conv import NEConv, NodeEdgeInt, adj2par1, degree, _bn_relu
 
 
@@ -102,6 +102,9 @@ class _Level:
         self.op_t = getattr(d, "op_t", None) or operator_for(d.edge_index_t.to(device), d.edge_weight_t.to(device), n)
         self.op_s = getattr(d, "op_s", None) or operator_for(d.edge_index_s.to(device), d.edge_weight_s.to(device), e)
         self.inc = getattr(d, "incidence", None) or incidence_for(d.edge_index.to(device), n)
+        if F_hl.factored_hodge1_enabled() and self.op_s.factored is None:
+            # opt-in: the caller asserts edge_index_s / edge_weight_s = 2 B1^T B1 / lambda_max (lib/Hodge_Dataset.py:456)
+            self.op_s.factored = Hodge1Factor.from_operator(self.op_s, self.inc)
         D = getattr(d, "D", None)
         self.D = (self.inc.degree() + eps) if D is None else D.to(device)   # degree(edge_index.view(-1), n) + 1e-6
         self.nv = (getattr(d, "n_valid_nodes", None), getattr(d, "n_valid_edges", None))

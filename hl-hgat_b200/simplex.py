@@ -59,6 +59,7 @@ class CsrOperator:
         self.nnz = int(edge_index.shape[1])
         self._ei, self._ew = edge_index, edge_weight
         self._fwd = self._bwd = None
+        self.factored = None            # optional Hodge1Factor: L1 = diag(s) B1^T B1 applied without the CSR
 
     @classmethod
     def from_csr(cls, rowptr, colidx, vals, nrows, symmetric=True, transpose=None):
@@ -67,6 +68,7 @@ class CsrOperator:
         op = cls.__new__(cls)
         op.nrows, op.nnz = int(nrows), int(colidx.numel())
         op._ei = op._ew = None
+        op.factored = None
         op._fwd = (rowptr, colidx, vals)
         op._bwd = op._fwd if symmetric else transpose
         return op
@@ -82,6 +84,25 @@ class CsrOperator:
         if self._bwd is None:
             self._bwd = csr_from_coo(self._ei[0], self._ei[1], self._ew, self.nrows)[:3]
         return self._bwd
+
+
+class Hodge1Factor:
+    """Factored form of an edge operator that IS the Hodge 1-Laplacian of the batch: L1 = diag(edge_scale) B1^T B1
+    with edge_scale[e] = 2 / lambda_max(graph of e) (lib/Hodge_Dataset.py:456).  Built by the GPU constructor
+    (which knows) or, for reference-format batches, from the operator's own diagonal (L1[e,e] = 2 edge_scale[e])
+    when the caller opts in (functional.enable_factored_hodge1)."""
+
+    def __init__(self, incidence, edge_scale):
+        self.incidence, self.edge_scale = incidence, edge_scale.contiguous()
+
+    @classmethod
+    def from_operator(cls, op, incidence):
+        rowptr, col, val = op.fwd
+        counts = (rowptr[1:] - rowptr[:-1]).long()
+        rows = torch.repeat_interleave(torch.arange(op.nrows, device=col.device), counts, output_size=int(col.numel()))
+        diag = torch.where(col.long() == rows, val, torch.zeros_like(val))
+        scale = torch.zeros(op.nrows, dtype=torch.float32, device=col.device).index_add_(0, rows, diag) * 0.5
+        return cls(incidence, scale)
 
 
 class Incidence:

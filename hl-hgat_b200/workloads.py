@@ -74,7 +74,7 @@ WORKLOADS = {
     "zinc": SimpleNamespace(
         model="HL_HGCNN_zinc_dense_int3_pyr",
         ctor=dict(channels=[2, 2, 2], filters=[64, 128, 256], mlp_channels=[], K=2, node_dim=21, edge_dim=3, keig=7),
-        batch=1024, cpu_sample=256, make=_zinc_batch, levels=1, deg_eps=0.0,
+        batch=1024, cpu_sample=256, make=_zinc_batch, levels=1, deg_eps=0.0, long_rows=False,
         loss=_graph_level(torch.nn.L1Loss()), label="zinc_pyr_train_b1024_K2_fp32",
         metric="train graphs/sec ZINC-shaped (HL_HGCNN_zinc_dense_int3_pyr, batch 1024/GPU, K=2, fp32)"),
     # configs[2]: main_pepfunc_HL_HGCNN_dense_int3_attpool.py:249-254 (script defaults)
@@ -82,7 +82,7 @@ WORKLOADS = {
         model="HL_HGCNN_pepfunc_dense_int3_attpool",
         ctor=dict(channels=[2, 2, 2], filters=[64, 128, 256], mlp_channels=[256], pool_loc=1, K=6, node_dim=9, edge_dim=3,
                   keig=10, num_classes=10),
-        batch=64, cpu_sample=16, make=_pep_batch, levels=2, deg_eps=1e-6,
+        batch=64, cpu_sample=16, make=_pep_batch, levels=2, deg_eps=1e-6, long_rows=False,
         loss=_attpool_loss(focal_loss), label="pepfunc_attpool_train_b64_K6_fp32",
         metric="train graphs/sec peptides-func-shaped (HL_HGCNN_pepfunc_dense_int3_attpool, batch 64/GPU, K=6, fp32)"),
     # configs[3]: lib/Hodge_ST_Model.py:958, main_cifar10SP_HL_HGCNN_dense_int3_attpool.py:36
@@ -90,14 +90,14 @@ WORKLOADS = {
         model="HL_HGCNN_CIFAR10SP_dense_int3_attpool",
         ctor=dict(channels=[2, 2, 2], filters=[64, 128, 256], mlp_channels=[256], K=4, node_dim=5, edge_dim=4, keig=10,
                   pool_loc=1, l=0.5, num_classes=10),
-        batch=256, cpu_sample=16, make=_cifar_batch, levels=2, deg_eps=1e-6,
+        batch=256, cpu_sample=16, make=_cifar_batch, levels=2, deg_eps=1e-6, long_rows=True,
         loss=_attpool_loss(torch.nn.CrossEntropyLoss()), label="cifar10sp_attpool_train_b256_K4_fp32",
         metric="train graphs/sec CIFAR10-superpixel-shaped (HL_HGCNN_CIFAR10SP_dense_int3_attpool, batch 256/GPU, K=4, fp32)"),
     # configs[4]: lib/Hodge_ST_Model.py:756, main_TSP_HL_HGCNN_dense_int3_pyr.py:38-48
     "tsp": SimpleNamespace(
         model="HL_HGCNN_TSP_dense_int3_pyr",
         ctor=dict(channels=[4, 4, 4], filters=[32, 64, 128], mlp_channels=[256], K=4, node_dim=2, edge_dim=1, num_classes=1),
-        batch=32, cpu_sample=1, make=_tsp_batch, levels=1, deg_eps=1e-6,
+        batch=32, cpu_sample=1, make=_tsp_batch, levels=1, deg_eps=1e-6, long_rows=True,
         loss=_tsp_loss, label="tsp_pyr_train_b32_K4_fp32",
         metric="train graphs/sec TSP-shaped (HL_HGCNN_TSP_dense_int3_pyr, 500-node kNN-25 graphs, batch 32/GPU, K=4, fp32)"),
 }

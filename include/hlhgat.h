@@ -141,6 +141,28 @@ int hl_poly_basis_bwd(int family, int K, const hl_conv_side* sides /* host */, i
                       hl_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Polynomial basis of the Hodge 1-Laplacian applied in FACTORED form (opt-in):
+ *   L1 = diag(edge_scale) B1^T B1,  edge_scale[e] = 2 / lambda_max(graph of e)   (lib/Hodge_Dataset.py:456: no B2 term)
+ *   (L1 x)[e] = edge_scale[e] * (y[head_e] - y[tail_e]),  y[n] = sum_{f incident to n} sgn(n,f) x[f]
+ * 4 row gathers per edge instead of one per nonzero of L1 (deg(tail)+deg(head)-1: ~18 CIFAR-superpixel, ~55 TSP).
+ * Same outputs as hl_poly_basis_fwd / _bwd on the CSR of that operator up to fp32 summation order (NOT bit for
+ * bit); the caller asserts that the edge operator of the batch is this Laplacian.  node_tmp: [n_nodes, width]
+ * scratch.  Replaces the same reference lines as hl_poly_basis_fwd/bwd for edge_index_s / edge_weight_s.
+ * -------------------------------------------------------------------------------------------- */
+typedef struct {
+  const int32_t* inc_rowptr;       /* node -> incident-edge CSR (ascending edge id) */
+  const int32_t* inc_edge;
+  const int32_t* tail;             /* [n_edges] */
+  const int32_t* head;
+  const float* edge_scale;         /* [n_edges] */
+  int32_t n_nodes, n_edges;
+} hl_hodge1_operator;
+int hl_poly_basis_hodge1_fwd(int family, int K, const hl_hodge1_operator* op /* host */, const float* x, int64_t ld_x,
+                             float* t, int64_t ld_t, int64_t t_stride, float* node_tmp, int32_t width, hl_stream_t stream);
+int hl_poly_basis_hodge1_bwd(int family, int K, const hl_hodge1_operator* op /* host */, float* g0, int64_t ld_g0,
+                             float* t, int64_t ld_t, int64_t t_stride, float* node_tmp, int32_t width, hl_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
  * Segmented (CSR-bucketed) row reduction with deterministic ascending order.
  *   dst[r,:] = post( sum_{p in [rowptr[r], rowptr[r+1])} pre(src[m_p, :]) ),  m_p = colidx ? colidx[p] : p
  *   pre  : src_scale ? src_scale[m] * v : v                  (attention gate, rounded before the sum)

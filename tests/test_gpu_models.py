@@ -164,3 +164,68 @@ def test_tsp_model_config_size_vs_oracle():
     close(pred, pred64.float(), rtol=1e-4, atol=1e-4 * float(pred_ref.abs().max()))
     g = torch.autograd.grad((pred * w.to(DEV)).sum() / w.shape[0], list(model.parameters()), allow_unused=True)
     print("tsp gradient error vs fp64 oracle: mean %.2e max %.2e" % _grad_report(model, g, g64))
+
+
+# ---------------------------------------------------------------------------------------------
+# factored Hodge 1-Laplacian (opt-in): L1 x = diag(s) B1^T (B1 x)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,batch,width", [("cifar", 6, 64), ("tsp", 2, 32), ("zinc", 40, 128), ("peptides", 5, 20), ("cifar", 3, 7)])
+@pytest.mark.parametrize("K", [2, 5])
+def test_factored_hodge1_basis_equals_csr_path(shape, batch, width, K):
+    from hlhgat_b200 import _native as N
+    from hlhgat_b200.simplex import CsrOperator, Hodge1Factor
+    b = make_batch(shape, batch, seed=13)
+    n, e = b.x_t.shape[0], b.x_s.shape[0]
+    op = CsrOperator(b.edge_index_s.to(DEV), b.edge_weight_s.to(DEV), e)
+    op.factored = Hodge1Factor.from_operator(op, incidence_for(b.edge_index.to(DEV), n))
+    torch.manual_seed(K)
+    x = torch.randn(e, width, device=DEV)
+    g0, gt = torch.randn(e, width, device=DEV), torch.randn(K - 1, e, width, device=DEV)
+    res = {}
+    try:
+        for flag in (False, True):
+            F_hl.enable_factored_hodge1(flag)
+            for fam in (N.HL_LAGUERRE, N.HL_CHEB):
+                (t,) = F_hl.poly_basis_fwd(fam, K, [op], [x], width)
+                a0, at = g0.clone(), gt.clone()
+                F_hl.poly_basis_bwd(fam, K, [op], [a0], [at], width)
+                res[(flag, fam)] = (t, a0, at)
+    finally:
+        F_hl.enable_factored_hodge1(False)
+    for fam in (N.HL_LAGUERRE, N.HL_CHEB):
+        for u, v in zip(res[(True, fam)], res[(False, fam)]):
+            close(u, v, rtol=1e-5, atol=2e-5 * float(v.abs().max()))
+
+
+def test_factored_hodge1_from_constructor_and_in_model():
+    """The GPU constructor attaches the factor itself; a TSP model step with the option on equals the CSR step."""
+    from hlhgat_b200.construct import build_simplex_batch
+    b = make_tsp_batch(2, seed=6, n=80, k=8)
+    ei = b.edge_index
+    sb = build_simplex_batch(torch.cat([ei[0], ei[1]]).to(DEV), torch.cat([ei[1], ei[0]]).to(DEV), b.num_node1)
+    ref = sb.op_s.fwd[2]
+    from hlhgat_b200.simplex import Hodge1Factor
+    derived = Hodge1Factor.from_operator(sb.op_s, sb.incidence)
+    close(sb.op_s.factored.edge_scale, derived.edge_scale, rtol=1e-6, atol=0)
+    assert ref.numel() > 0
+    ctor = dict(channels=[1, 1], filters=[32, 64], mlp_channels=[32], K=4, node_dim=2, edge_dim=1, num_classes=1)
+    torch.manual_seed(0)
+    model = M.HL_HGCNN_TSP_dense_int3_pyr(**ctor).to(DEV).train()
+    d = to_dev(b)
+    w = torch.randn(b.x_s.shape[0], 1, device=DEV)
+    outs = []
+    try:
+        for flag in (False, True):
+            F_hl.enable_factored_hodge1(flag)
+            from hlhgat_b200.simplex import clear_caches
+            clear_caches()
+            pred, _ = model(d, device=DEV)
+            g = torch.autograd.grad((pred * w).sum(), [p for p in model.parameters()], allow_unused=True)
+            outs.append((pred, g))
+    finally:
+        F_hl.enable_factored_hodge1(False)
+    close(outs[1][0], outs[0][0], rtol=1e-4, atol=1e-4 * float(outs[0][0].abs().max()))
+    gmax = max(float(c.norm()) for c in outs[0][1] if c is not None)
+    for a, c in zip(outs[1][1], outs[0][1]):
+        if c is not None and float(c.norm()) > 1e-4 * gmax:        # (biases in front of a BatchNorm: pure rounding noise)
+            assert float((a - c).norm()) < 2e-3 * float(c.norm())

@@ -18,9 +18,14 @@ wl = WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "zinc"]
 dev = torch.device("cuda:0")
 model = getattr(M, wl.model)(**wl.ctor).to(dev).train()
 bucket = FlatGradBucket(model.parameters())
+from hlhgat_b200.training import pad_levels  # noqa: E402
 raw = [wl.make(wl.batch, 0)]
-cap = Capacity.covering(raw)
-sb = StaticBatch(pad_batch(raw[0], cap, deg_eps=wl.deg_eps), dev)
+if wl.levels > 1:
+    caps = [Capacity.covering([raw[0][l]]) for l in range(wl.levels)]
+    sb = StaticBatch(pad_levels(raw[0], caps, deg_eps=wl.deg_eps), dev)
+else:
+    cap = Capacity.covering(raw)
+    sb = StaticBatch(pad_batch(raw[0], cap, deg_eps=wl.deg_eps), dev)
 
 
 from hlhgat_b200.functional import accumulate_into_grads  # noqa: E402
