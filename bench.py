@@ -168,7 +168,7 @@ def ncu_traffic_bytes():
 # ------------------------------------------------------------------------------------------------
 ROOFLINE_CASES = {
     # workload: (block-diagonal replication, feature width): sized so inputs + outputs exceed the 126 MB L2
-    "zinc": (16, 64), "peptides": (40, 64), "cifar": (4, 64), "tsp": (4, 32),
+    "zinc": (16, 64), "zinc_default": (16, 64), "peptides": (40, 64), "cifar": (4, 64), "tsp": (4, 32),
 }
 
 
@@ -208,7 +208,7 @@ def spmm_roofline(dev, batch_dev, workload="zinc", iters=20):
            "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": ms * 1e3,
            "workload": f"{workload}-shaped bench batch x{reps} block-diagonal, rows {rows_tot}, nnz {nnz_tot}, F={width}; "
                        "inputs+outputs > L2"}
-    if workload == "zinc":
+    if workload.startswith("zinc"):
         out["traffic"] = ncu_traffic_bytes()
         out["traffic_source"] = "profiles/r1_spmm_v3_staged_full.txt (ncu --set full of tools/spmm_probe.py, same operator stack)"
     return out
@@ -356,7 +356,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="zinc", choices=["zinc", "peptides", "cifar", "tsp"],
+    ap.add_argument("--workload", default="zinc", choices=["zinc", "zinc_default", "peptides", "cifar", "tsp"],
                     help="BASELINE.json config: zinc = configs[1] (the headline metric, default); the others are the "
                          "peptides-func / CIFAR10-superpixel / TSP-shaped configs")
     ap.add_argument("--pool", type=int, default=POOL, help="distinct synthetic batches cycled through")
