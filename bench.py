@@ -232,6 +232,7 @@ def run_ours(args, world, rank, local):
     factored = args.factored_l1 == "on" or (args.factored_l1 == "auto" and wl.long_rows)
     from hlhgat_b200 import functional as F_hl
     F_hl.enable_factored_hodge1(factored)
+    hlhgat_b200.enable_lanes(args.lanes == "on")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     torch.manual_seed(0)
@@ -316,7 +317,9 @@ def run_ours(args, world, rank, local):
                        "l2": "no explicit flush: per-step working set (activations saved for backward, ~1 GB or more) exceeds the "
                              "126 MB L2 and consecutive steps use different batches",
                        "execution": "whole step (CSR bucketing + forward + backward) replayed as one CUDA graph on batches padded "
-                                    f"to a fixed capacity ({cap_txt}, ~2% ghost rows), then all-reduce + fused Adam graph",
+                                    f"to a fixed capacity ({cap_txt}, ~2% ghost rows), then all-reduce + fused Adam graph"
+                                    + ("; node chain and edge chain of every layer on two streams = two parallel branches of the graph"
+                                       if args.lanes == "on" else ""),
                        "edge_operator": ("L1 applied in factored form diag(2/lambda) B1^T B1 (opt-in, fp32-rounding-equal to the CSR path)"
                                          if factored else "L1 applied from its CSR (bit-exact summation order of the reference)"),
                        "gemm": "dense Theta/MLP transforms + data/weight gradients: hand-written tcgen05 3xTF32 kernels (fp32-accurate); "
@@ -360,6 +363,8 @@ def main():
                     help="BASELINE.json config: zinc = configs[1] (the headline metric, default); the others are the "
                          "peptides-func / CIFAR10-superpixel / TSP-shaped configs")
     ap.add_argument("--pool", type=int, default=POOL, help="distinct synthetic batches cycled through")
+    ap.add_argument("--lanes", default="on", choices=["on", "off"],
+                    help="issue the node chain and the edge chain of every layer on two CUDA streams (bit-identical results)")
     ap.add_argument("--factored-l1", default="auto", choices=["auto", "on", "off"],
                     help="apply the edge Laplacian as diag(2/lambda) B1^T B1 instead of its CSR; auto = only for the long-row "
                          "workloads (cifar, tsp); the ZINC headline always uses the CSR SpMM")

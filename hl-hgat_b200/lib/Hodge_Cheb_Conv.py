@@ -4,6 +4,7 @@ Same class names, constructor arguments, attribute / state_dict names and forwar
 as the reference; the arithmetic runs in libhlhgat.so (sm_100a) -- CUDA tensors only, no
 PyG / torch_scatter / torch_sparse, no CPU fallback.
 """
+import contextlib
 import math
 
 import torch
@@ -12,6 +13,7 @@ from torch import Tensor
 from torch.nn import Parameter
 
 from .. import functional as F_hl
+from .. import lanes as _lanes
 from .. import _native as N
 from ..simplex import operator_for, incidence_for, CsrOperator, Incidence
 
@@ -218,6 +220,17 @@ class NodeEdgeInt(nn.Module):
 
     def forward(self, x_t, x_s, par, D, nvalid=(None, None)):
         inc = _incidence_of(par)
+        ln = _lanes.active()
+        if ln is not None and not self.only_att:
+            # two-lane issue (lanes.py): the node MLP stays on the node lane, the edge MLP goes to the edge lane;
+            # the transfers are the only place where a lane reads the other lane's features
+            ln.exchange(node_tensors=(x_t,), edge_tensors=(x_s,))
+            x_t1 = _mlp(self.WV_Node, F_hl.edge_to_node(x_s, D, inc), x_t, nvalid[0])
+            with ln.edge_ctx():
+                x_s1 = _mlp(self.WV_Edge, F_hl.node_to_edge(x_t, inc), x_s, nvalid[1])
+            return x_t1, x_s1
+        if ln is not None:
+            ln.to_node(x_s)                # the gate is computed on the node lane
         x_s2t = F_hl.edge_to_node(x_s, D, inc)
         x_t2s = F_hl.node_to_edge(x_t, inc)
         if self.only_att:
@@ -297,11 +310,14 @@ class NEConv(nn.Module):
         self.slope, self.p = slope, dropout_ratio
 
     def forward(self, x_t, edge_index_t, edge_weight_t, x_s, edge_index_s, edge_weight_s, nvalid=(None, None)):
+        ln = _lanes.active()
         x_t = self.module_1.forward_act(self.module_0(x_t, edge_index_t, edge_weight_t), self.slope, nvalid[0])
-        x_s = self.module_5.forward_act(self.module_4(x_s, edge_index_s, edge_weight_s), self.slope, nvalid[1])
         if self.p > 0.0:
             x_t = torch.nn.functional.dropout(x_t, self.p, self.training)
-            x_s = torch.nn.functional.dropout(x_s, self.p, self.training)
+        with (ln.edge_ctx() if ln is not None else contextlib.nullcontext()):   # x_s lives on the edge lane (lanes.py)
+            x_s = self.module_5.forward_act(self.module_4(x_s, edge_index_s, edge_weight_s), self.slope, nvalid[1])
+            if self.p > 0.0:
+                x_s = torch.nn.functional.dropout(x_s, self.p, self.training)
         return [x_t, x_s]
 
 

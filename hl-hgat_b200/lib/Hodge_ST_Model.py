@@ -1,12 +1,30 @@
 """Callers of the hot path, kept API- and state_dict-compatible with the reference's
 lib/Hodge_ST_Model.py so existing checkpoints load with strict=True.  Only the classes the
 BASELINE.json configs drive are mirrored here."""
+import contextlib
+
 import torch
 import torch.nn as nn
 
 from .. import functional as F_hl
+from .. import lanes as _lanes
 from ..simplex import Hodge1Factor, incidence_for, operator_for
 from .Hodge_Cheb_Conv import NEConv, NodeEdgeInt, adj2par1, degree, _bn_relu
+
+
+def _share_tables(ln, op_s, inc):
+    """Tables built on the node lane that the edge lane reads too (lanes.py: record_stream at the crossing)."""
+    if ln is None:
+        return
+    tabs = [inc.tail, inc.head, inc.rowptr, inc.edge]
+    for csr in (op_s._fwd, op_s._bwd):
+        if csr is not None:
+            tabs += [t for t in csr if t is not None]
+    if op_s.factored is not None:
+        tabs.append(op_s.factored.edge_scale)
+        fi = op_s.factored.incidence
+        tabs += [fi.tail, fi.head, fi.rowptr, fi.edge]
+    ln.to_edge(*tabs)
 
 
 class _MlpBlock(nn.Sequential):
@@ -55,18 +73,27 @@ class HL_HGCNN_zinc_dense_int3_pyr(nn.Module):
         op_s = operator_for(data.edge_index_s, data.edge_weight_s, e)
         seg_t = F_hl.Segments.from_counts(torch.as_tensor(data.num_node1, device=x_t.device), total=n)
         seg_s = F_hl.Segments.from_counts(torch.as_tensor(data.num_edge1, device=x_t.device), total=e)
-        x_t, x_s = self.HL_init_conv(x_t, op_t, None, x_s, op_s, None, nv)
-        x_s0, x_t0 = x_s, x_t
         inc = incidence_for(data.edge_index, n)
         D = getattr(data, "D", None)
         if D is None:
             D = inc.degree()                # = degree(edge_index.view(-1)) of :624 (no 1e-6 in this model)
-        for i, _ in enumerate(self.channels):
-            for j in range(self.channels[i]):
-                x_t, x_s = getattr(self, f"NEInt{i}{j}")(x_t0, x_s0, inc, D, nv)
-                x_t, x_s = getattr(self, f"NEConv{i}{j}")(x_t, op_t, None, x_s, op_s, None, nv)
-                x_t0 = torch.cat([x_t0, x_t], dim=-1)
-                x_s0 = torch.cat([x_s0, x_s], dim=-1)
+        with _lanes.open_lanes(x_t.device) as ln:      # ln is None unless lanes.enable_lanes(): single stream
+            edge = ln.edge_ctx if ln is not None else contextlib.nullcontext
+            _share_tables(ln, op_s, inc)
+            x_t, x_s = self.HL_init_conv(x_t, op_t, None, x_s, op_s, None, nv)
+            x_s0, x_t0 = x_s, x_t
+            last = (len(self.channels) - 1, self.channels[-1] - 1)
+            for i, _ in enumerate(self.channels):
+                for j in range(self.channels[i]):
+                    x_t, x_s = getattr(self, f"NEInt{i}{j}")(x_t0, x_s0, inc, D, nv)
+                    x_t, x_s = getattr(self, f"NEConv{i}{j}")(x_t, op_t, None, x_s, op_s, None, nv)
+                    if (i, j) == last:
+                        break              # the dense-connection buffers of the last layer are never read (:627-636)
+                    x_t0 = torch.cat([x_t0, x_t], dim=-1)
+                    with edge():
+                        x_s0 = torch.cat([x_s0, x_s], dim=-1)
+            if ln is not None:
+                ln.to_node(x_s)
         x = torch.cat((F_hl.segment_mean(x_s, seg_s), F_hl.segment_mean(x_t, seg_t)), -1)
         for i, _ in enumerate(self.mlp_channels):
             x = getattr(self, "mlp%d" % i)(x, nv_g)
@@ -118,12 +145,23 @@ class _Level:
 
 
 def _stage(self, i, lv, x_t0, x_s0):
+    """One stage of NEInt / NEConv layers with dense connections.  With lanes enabled (lanes.py) the edge chain is
+    issued on the edge lane; the stage hands everything back to the node lane at its end (gates, pooling and
+    the head run there)."""
     x_t = x_s = None
+    ln = _lanes.active()
+    edge = ln.edge_ctx if ln is not None else contextlib.nullcontext
+    if ln is not None:
+        _share_tables(ln, lv.op_s, lv.inc)
+        ln.to_edge(x_s0)
     for j in range(self.channels[i]):
         x_t, x_s = getattr(self, f"NEInt{i}{j}")(x_t0, x_s0, lv.inc, lv.D, lv.nv)
         x_t, x_s = getattr(self, f"NEConv{i}{j}")(x_t, lv.op_t, None, x_s, lv.op_s, None, lv.nv)
         x_t0 = torch.cat([x_t0, x_t], dim=-1)
-        x_s0 = torch.cat([x_s0, x_s], dim=-1)
+        with edge():
+            x_s0 = torch.cat([x_s0, x_s], dim=-1)
+    if ln is not None:
+        ln.to_node(x_s, x_s0)
     return x_t, x_s, x_t0, x_s0
 
 
@@ -168,10 +206,12 @@ class HL_HGCNN_TSP_dense_int3_pyr(nn.Module):
         x_t = data.x_t
         x_s, edge_mask = data.x_s[:, :1], data.x_s[:, 1:]
         lv = _Level(data, x_t.shape[0], x_s.shape[0], 1e-6, x_t.device)
-        x_t, x_s = self.HL_init_conv(x_t, lv.op_t, None, x_s, lv.op_s, None, lv.nv)
-        x_t0, x_s0 = x_t, x_s
-        for i, _ in enumerate(self.channels):
-            x_t, x_s, x_t0, x_s0 = _stage(self, i, lv, x_t0, x_s0)
+        with _lanes.open_lanes(x_t.device) as ln:
+            _share_tables(ln, lv.op_s, lv.inc)
+            x_t, x_s = self.HL_init_conv(x_t, lv.op_t, None, x_s, lv.op_s, None, lv.nv)
+            x_t0, x_s0 = x_t, x_s
+            for i, _ in enumerate(self.channels):
+                x_t, x_s, x_t0, x_s0 = _stage(self, i, lv, x_t0, x_s0)
         x_s = torch.cat([x_s, F_hl.boundary_absdiff(x_t, lv.inc)], dim=-1)
         if len(self.mlp_channels) == 1:
             x_s = self.mlp(x_s, lv.op_s, lv.nv[1])
@@ -230,19 +270,21 @@ class HL_HGCNN_CIFAR10SP_dense_int3_attpool(_AttPool):
         lv = _Level(d0, d0.x_t.shape[0], d0.x_s.shape[0], 1e-6, dev)
         n1, e1 = d1.x_t.shape[0], d1.x_s.shape[0]
         seg_pt, seg_ps = self._positions(datas, lv, n1, e1, dev)
-        x_t, x_s = self.HL_init_conv(d0.x_t[:, 1:], lv.op_t, None, d0.x_s[:, 1:], lv.op_s, None, lv.nv)
-        x_t0, x_s0 = x_t, x_s
-        att_t = att_s = None
-        for i, _ in enumerate(self.channels):
-            x_t, x_s, x_t0, x_s0 = _stage(self, i, lv, x_t0, x_s0)
-            if i == self.pool_loc:
-                att_t, att_s = getattr(self, "NEAtt%d" % i)(x_t, x_s, lv.inc, lv.D)
-                att_t = att_t / att_t.max()
-                att_s = att_s / att_s.max()
-                x_t, x_s = x_t * att_t, x_s * att_s
-                x_t0 = F_hl.segment_mean(x_t0, seg_pt)
-                x_s0 = F_hl.segment_mean(x_s0, seg_ps)
-                lv = _Level(d1, n1, e1, 1e-6, dev)
+        with _lanes.open_lanes(dev) as ln:
+            _share_tables(ln, lv.op_s, lv.inc)
+            x_t, x_s = self.HL_init_conv(d0.x_t[:, 1:], lv.op_t, None, d0.x_s[:, 1:], lv.op_s, None, lv.nv)
+            x_t0, x_s0 = x_t, x_s
+            att_t = att_s = None
+            for i, _ in enumerate(self.channels):
+                x_t, x_s, x_t0, x_s0 = _stage(self, i, lv, x_t0, x_s0)
+                if i == self.pool_loc:
+                    att_t, att_s = getattr(self, "NEAtt%d" % i)(x_t, x_s, lv.inc, lv.D)
+                    att_t = att_t / att_t.max()
+                    att_s = att_s / att_s.max()
+                    x_t, x_s = x_t * att_t, x_s * att_s
+                    x_t0 = F_hl.segment_mean(x_t0, seg_pt)
+                    x_s0 = F_hl.segment_mean(x_s0, seg_ps)
+                    lv = _Level(d1, n1, e1, 1e-6, dev)
         x = self._head(x_t, x_s, lv)
         if if_final_layer:
             return x, self.out(x)
@@ -275,20 +317,22 @@ class HL_HGCNN_pepfunc_dense_int3_attpool(_AttPool):
         lv = _Level(d0, d0.x_t.shape[0], d0.x_s.shape[0], 1e-6, dev)
         n1, e1 = d1.x_t.shape[0], d1.x_s.shape[0]
         seg_pt, seg_ps = self._positions(datas, lv, n1, e1, dev)
-        x_t, x_s = self.HL_init_conv(d0.x_t[:, 1:], lv.op_t, None, d0.x_s[:, 1:], lv.op_s, None, lv.nv)
-        x_t0, x_s0 = x_t, x_s
-        last = len(self.channels) - 1
-        for i, _ in enumerate(self.channels):
-            x_t, x_s, x_t0, x_s0 = _stage(self, i, lv, x_t0, x_s0)
-            if i == last and not if_att:
-                break                      # the last gate only rescales buffers nothing reads (:131-134 then :150)
-            att_t, att_s = getattr(self, "NEAtt%d" % i)(x_t0, x_s0, lv.inc, lv.D)
-            if i == self.pool_loc:
-                x_t0 = F_hl.segment_mean(x_t0, seg_pt, att_t)
-                x_s0 = F_hl.segment_mean(x_s0, seg_ps, att_s)
-                lv = _Level(d1, n1, e1, 1e-6, dev)
-            elif i != last:
-                x_t0, x_s0 = x_t0 * att_t, x_s0 * att_s
+        with _lanes.open_lanes(dev) as ln:
+            _share_tables(ln, lv.op_s, lv.inc)
+            x_t, x_s = self.HL_init_conv(d0.x_t[:, 1:], lv.op_t, None, d0.x_s[:, 1:], lv.op_s, None, lv.nv)
+            x_t0, x_s0 = x_t, x_s
+            last = len(self.channels) - 1
+            for i, _ in enumerate(self.channels):
+                x_t, x_s, x_t0, x_s0 = _stage(self, i, lv, x_t0, x_s0)
+                if i == last and not if_att:
+                    break                      # the last gate only rescales buffers nothing reads (:131-134 then :150)
+                att_t, att_s = getattr(self, "NEAtt%d" % i)(x_t0, x_s0, lv.inc, lv.D)
+                if i == self.pool_loc:
+                    x_t0 = F_hl.segment_mean(x_t0, seg_pt, att_t)
+                    x_s0 = F_hl.segment_mean(x_s0, seg_ps, att_s)
+                    lv = _Level(d1, n1, e1, 1e-6, dev)
+                elif i != last:
+                    x_t0, x_s0 = x_t0 * att_t, x_s0 * att_s
         x = self._head(x_t, x_s, lv)
         if if_att:
             return self.out(x), att_t, att_s

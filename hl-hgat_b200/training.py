@@ -14,6 +14,7 @@ from types import SimpleNamespace
 
 import torch
 
+from . import lanes
 from .functional import accumulate_into_grads
 from .simplex import clear_caches
 
@@ -175,6 +176,7 @@ class GraphedTrainStep:
             loss = self.criterion(pred[:g], self.batch.y)
         with accumulate_into_grads():              # weight gradients land in the flat bucket directly
             loss.backward()
+        lanes.join(self.device)                     # edge-lane weight gradients land in the bucket before the all-reduce
         self.loss.copy_(loss.detach())
 
     def step(self):

@@ -88,3 +88,18 @@ def test_pairdata_collate_matches_reference_batch():
     assert bb.num_graphs == len(graphs) and bb.num_nodes == off_n and bb.ptr[-1] == off_n
     levels = collate([[g, g] for g in graphs])
     assert isinstance(levels, list) and len(levels) == 2 and torch.equal(levels[1].edge_index_s, b["edge_index_s"])
+
+
+def test_lanes_are_inert_without_cuda_tensors():
+    """lanes.open_lanes yields None (single stream) unless enabled AND on a CUDA device; join is a no-op then."""
+    from hlhgat_b200 import lanes
+    assert not lanes.lanes_enabled() and lanes.active() is None
+    with lanes.open_lanes("cpu") as ln:
+        assert ln is None
+    lanes.enable_lanes(True)
+    try:
+        with lanes.open_lanes("cpu") as ln:
+            assert ln is None and lanes.active() is None
+    finally:
+        lanes.enable_lanes(False)
+    lanes.join()
