@@ -3,12 +3,14 @@
 Forward and backward both run hand-written sm_100a kernels from libhlhgat.so; the only library
 calls are the dense Theta / MLP GEMMs (cuBLAS through torch.mm), as DESIGN.md states.
 """
+import contextlib
 import ctypes as C
 import math
 
 import torch
 
 from . import _native as N
+from . import lanes as _lanes
 from .simplex import CsrOperator, Hodge1Factor, Incidence, csr_from_coo  # noqa: F401
 
 _FAMILY = {"laguerre": N.HL_LAGUERRE, "cheb": N.HL_CHEB}
@@ -126,6 +128,13 @@ def _grad_target(p):
     if g.dim() == 2 and g.stride(0) < g.shape[1]:
         return None
     return g
+
+
+def _wgrad_lane(fused, *tensors):
+    """Context for issuing a weight / bias gradient: the lane's auxiliary stream when the result is accumulated
+    in place into `param.grad` (nothing in the autograd graph waits for it; lanes.weight_grad_lane), else the
+    current stream."""
+    return _lanes.weight_grad_lane(*tensors) if fused else contextlib.nullcontext()
 
 
 def dense(a, w, bias=None, out=None, accumulate=False, transpose_w=False):
@@ -261,23 +270,25 @@ class _Linear(torch.autograd.Function):
         g = g.contiguous()
         d = xa.shape[1]
         ga = gb = gw = gbias = None
-        if ctx.needs_input_grad[0]:
-            ga = dense(g, weight[:, :d], transpose_w=True)
-        if xb is not None and ctx.needs_input_grad[1]:
-            gb = dense(g, weight[:, d:], transpose_w=True)
         if ctx.needs_input_grad[2]:
             tgt = _grad_target(ctx.params[0])
-            gw = torch.empty_like(weight) if tgt is None else tgt
-            wgrad(g, xa, gw[:, :d], accumulate=tgt is not None)
-            if xb is not None:
-                wgrad(g, xb, gw[:, d:], accumulate=tgt is not None)
+            with _wgrad_lane(tgt is not None, g, xa, xb):
+                gw = torch.empty_like(weight) if tgt is None else tgt
+                wgrad(g, xa, gw[:, :d], accumulate=tgt is not None)
+                if xb is not None:
+                    wgrad(g, xb, gw[:, d:], accumulate=tgt is not None)
             if tgt is not None:
                 gw = None
         if ctx.has_bias and ctx.needs_input_grad[3]:
             tgt = _grad_target(ctx.params[1])
-            gbias = colsum(g, out=tgt)
+            with _wgrad_lane(tgt is not None, g):
+                gbias = colsum(g, out=tgt)
             if tgt is not None:
                 gbias = None
+        if ctx.needs_input_grad[0]:
+            ga = dense(g, weight[:, :d], transpose_w=True)
+        if xb is not None and ctx.needs_input_grad[1]:
+            gb = dense(g, weight[:, d:], transpose_w=True)
         return ga, gb, gw, gbias
 
 
@@ -318,6 +329,23 @@ class _PolyConv(torch.autograd.Function):
         R, width = x.shape
         g = g.contiguous()
         need_x = ctx.needs_input_grad[0]
+        gws = []
+        for k in range(K):
+            if ctx.needs_input_grad[5 + k]:
+                src = x if k == 0 else t[k - 1]
+                tgt = _grad_target(ctx.params[1][k])
+                with _wgrad_lane(tgt is not None, g, src):
+                    gw = wgrad(g, src.view(-1, inner), out=tgt, accumulate=tgt is not None)
+                gws.append(None if tgt is not None else gw)
+            else:
+                gws.append(None)
+        gb = None
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            tgt = _grad_target(ctx.params[0])
+            with _wgrad_lane(tgt is not None, g):
+                gb = colsum(g, out=tgt)
+            if tgt is not None:
+                gb = None
         gx = None
         if need_x:
             g0 = dense(g, weights[0], transpose_w=True).view(R, width)
@@ -326,21 +354,6 @@ class _PolyConv(torch.autograd.Function):
                 dense(g, weights[k], out=gt[k - 1].view(-1, inner), transpose_w=True)
             poly_basis_bwd(ctx.family, K, [op], [g0], [gt], width)
             gx = g0
-        gws = []
-        for k in range(K):
-            if ctx.needs_input_grad[5 + k]:
-                src = x if k == 0 else t[k - 1]
-                tgt = _grad_target(ctx.params[1][k])
-                gw = wgrad(g, src.view(-1, inner), out=tgt, accumulate=tgt is not None)
-                gws.append(None if tgt is not None else gw)
-            else:
-                gws.append(None)
-        gb = None
-        if ctx.has_bias and ctx.needs_input_grad[1]:
-            tgt = _grad_target(ctx.params[0])
-            gb = colsum(g, out=tgt)
-            if tgt is not None:
-                gb = None
         return (gx, gb, None, None, None, *gws)
 
 

@@ -25,6 +25,8 @@ import torch
 
 _STATE = {"enabled": False, "active": None, "dirty": False}
 _SIDE = {}          # device index -> the edge-lane stream (created once; a captured graph keeps using it)
+_AUX = {}           # (device index, lane stream handle) -> that lane's weight-gradient stream
+_AUX_USED = []      # aux streams with work issued since the last join()
 
 
 def enable_lanes(flag=True):
@@ -101,6 +103,30 @@ def open_lanes(device):
         ln.node.wait_stream(ln.edge)
 
 
+@contextlib.contextmanager
+def weight_grad_lane(*tensors):
+    """Backward pass, fused-accumulation mode only (functional.accumulate_into_grads): weight / bias gradients are
+    added straight into the flat bucket and nothing downstream in the autograd graph reads them, so they leave the
+    critical chain (data gradient -> BatchNorm backward -> ...) and are issued on an auxiliary stream of the current
+    lane -- one more parallel branch of the whole-step graph, ordered after everything issued so far on the lane
+    and joined by `join()`.  `tensors` (the operands the side stream reads) are `record_stream`-ed."""
+    if not _STATE["enabled"]:
+        yield
+        return
+    cur = torch.cuda.current_stream()
+    key = (cur.device.index, cur.cuda_stream)
+    aux = _AUX.get(key)
+    if aux is None:
+        aux = _AUX[key] = torch.cuda.Stream(device=cur.device)
+    aux.wait_stream(cur)
+    Lanes._mark(aux, tensors)
+    if aux not in _AUX_USED:
+        _AUX_USED.append(aux)
+    _STATE["dirty"] = True
+    with torch.cuda.stream(aux):
+        yield
+
+
 def join(device=None):
     """After `loss.backward()`: the current stream waits for the edge lane (weight gradients accumulated straight
     into the flat bucket bypass autograd's own end-of-backward stream sync)."""
@@ -108,6 +134,10 @@ def join(device=None):
         return
     _STATE["dirty"] = False
     idx = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+    cur = torch.cuda.current_stream(idx)
     side = _SIDE.get(idx)
     if side is not None:
-        torch.cuda.current_stream(idx).wait_stream(side)
+        cur.wait_stream(side)
+    for aux in _AUX_USED:
+        cur.wait_stream(aux)
+    _AUX_USED.clear()

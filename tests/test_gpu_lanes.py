@@ -46,13 +46,15 @@ def _run(model, loss_of, use_lanes, reps=1):
 
 def _assert_same(a, b, exact_grads=True):
     assert torch.equal(a[0], b[0]), (float(a[0]), float(b[0]))
+    scale = max(float(y.abs().max()) for y in b[1] if y is not None)
     for x, y in zip(a[1], b[1]):
         assert (x is None) == (y is None)
         if x is not None and exact_grads:
             assert torch.equal(x, y)
         elif x is not None:
-            # biases in front of a BatchNorm have a zero true gradient (pure rounding noise ~1e-8): absolute floor
-            assert float((x - y).norm()) <= 1e-5 * float(y.norm()) + 1e-7 * y.numel() ** 0.5
+            # biases in front of a BatchNorm have a zero true gradient (pure rounding noise): floor on the scale
+            # of the largest gradient entry of the model
+            assert float((x - y).norm()) <= 1e-5 * float(y.norm()) + 1e-6 * scale * y.numel() ** 0.5
     for x, y in zip(a[2], b[2]):
         assert torch.equal(x, y)
 
