@@ -33,6 +33,11 @@ class ConvSide(C.Structure):
                 ("x", _vp), ("ld_x", _i64), ("t", _vp), ("ld_t", _i64), ("t_stride", _i64), ("g0", _vp), ("ld_g0", _i64)]
 
 
+class SplitDesc(C.Structure):
+    _fields_ = [("src", _vp), ("hi", _vp), ("lo", _vp), ("ld_src", _i64), ("ld_out", _i64),
+                ("rows", _i32), ("cols", _i32), ("transpose", _i32), ("reserved", _i32)]
+
+
 class Hodge1Operator(C.Structure):
     _fields_ = [("inc_rowptr", _vp), ("inc_edge", _vp), ("tail", _vp), ("head", _vp), ("edge_scale", _vp),
                 ("n_nodes", _i32), ("n_edges", _i32)]
@@ -65,6 +70,7 @@ _SIGNATURES = {
     "hl_laplacian_rowptr": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hl_laplacian_fill": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hl_tf32_split": (C.c_int, [_vp, _i64, _i32, _i32, C.c_int, _vp, _vp, _i64, _vp]),
+    "hl_tf32_split_batch": (C.c_int, [_vp, _i32, _i64, _vp]),
     "hl_gemm_tf32x3": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _i64, C.c_int, _vp]),
     "hl_gemm2_tf32x3": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _i64, C.c_int, _vp]),
     "hl_wgrad_tf32x3_workspace": (_sz, [_i32, _i32, _i32]),

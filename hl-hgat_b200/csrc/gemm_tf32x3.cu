@@ -325,6 +325,21 @@ __global__ void tf32_split_kernel(const float* __restrict__ src, int64_t ld_src,
   }
 }
 
+// the same split for a whole table of weight views in one launch: blockIdx.y = table entry
+__global__ void __launch_bounds__(256)
+tf32_split_batch_kernel(const hl_split_desc* __restrict__ table) {
+  const hl_split_desc D = table[blockIdx.y];
+  const int64_t n = (int64_t)D.rows * D.cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / D.cols), c = (int)(i - (int64_t)r * D.cols);
+    const float x = D.src[(int64_t)r * D.ld_src + c];
+    const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    const int64_t o = D.transpose ? (int64_t)c * D.ld_out + r : (int64_t)r * D.ld_out + c;
+    D.hi[o] = h;
+    D.lo[o] = x - h;
+  }
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;
@@ -366,6 +381,18 @@ extern "C" int hl_tf32_split(const float* src, int64_t ld_src, int32_t rows, int
   if (blocks > 148 * 8) blocks = 148 * 8;
   tf32_split_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(src, ld_src, rows, cols, transpose, hi, lo, ld_out);
   HL_LAUNCH_CHECK("tf32_split_kernel");
+  return HL_OK;
+}
+
+extern "C" int hl_tf32_split_batch(const hl_split_desc* table, int32_t n_entries, int64_t max_elements, hl_stream_t stream) {
+  using namespace hl;
+  if (n_entries < 0 || max_elements < 0) return HL_ERR_INVALID;
+  if (n_entries == 0 || max_elements == 0) return HL_OK;
+  if (!table || n_entries > 65535) return HL_ERR_INVALID;
+  int64_t bx = (max_elements + 255) / 256;
+  if (bx > 32) bx = 32;
+  tf32_split_batch_kernel<<<dim3((unsigned)bx, (unsigned)n_entries), 256, 0, as_stream(stream)>>>(table);
+  HL_LAUNCH_CHECK("tf32_split_batch_kernel");
   return HL_OK;
 }
 

@@ -137,6 +137,100 @@ def _wgrad_lane(fused, *tensors):
     return _lanes.weight_grad_lane(*tensors) if fused else contextlib.nullcontext()
 
 
+class WeightSplitPlan:
+    """Takes the tf32 hi / lo split of the weights off the critical chain of a training step.
+
+    Every tensor-core GEMM needs its weight operand pre-split (`hl_tf32_split`, a few microseconds, ~130 launches per
+    ZINC step), and weights change only in the optimizer step.  Inside `with plan:` the first pass RECORDS every
+    split request (which parameter view, transposed or not, packed with which second view) and keeps its hi / lo
+    buffers; every later `with plan:` re-issues all recorded splits up front on the plan's own stream -- one more
+    parallel branch of the whole-step graph, overlapping the CSR bucketing -- and the GEMM call sites just wait for
+    its event and read the persistent buffers.  Parameter storage must stay in place (in-place optimizer updates,
+    `load_state_dict`); call `clear()` after anything that re-allocates parameters."""
+
+    def __init__(self):
+        self.entries = {}          # key -> (views kept alive, hi, lo, [hl_tf32_split argument tuples])
+        self.stream = None
+        self.ready = None
+        self._table = None         # device copy of the descriptor table (rebuilt when entries were added)
+        self._table_len = 0
+        self._max_elements = 0
+
+    def clear(self):
+        self.entries.clear()
+        self._table, self._table_len = None, 0
+
+    def _build_table(self, device):
+        descs = [a for _, _, _, launches in self.entries.values() for a in launches]
+        arr = (N.SplitDesc * len(descs))()
+        for d, (src, ld_src, rows, cols, tr, hi, lo, ld_out) in zip(arr, descs):
+            d.src, d.hi, d.lo, d.ld_src, d.ld_out, d.rows, d.cols, d.transpose = src, hi, lo, ld_src, ld_out, rows, cols, tr
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self._table = raw.to(device)
+        self._table_len = len(descs)
+        self._n_entries = len(self.entries)
+        self._max_elements = max(r * c for _, _, r, c, *_ in descs)
+
+    def __enter__(self):
+        global _PLAN
+        assert _PLAN is None, "WeightSplitPlan scopes do not nest"
+        _PLAN = self
+        self.ready = None
+        if self.entries and self._table is not None and self._n_entries == len(self.entries):
+            cur = torch.cuda.current_stream()
+            if self.stream is None:
+                self.stream = torch.cuda.Stream(device=cur.device)
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                N.check(N.lib().hl_tf32_split_batch(self._table.data_ptr(), self._table_len, self._max_elements, N.stream_ptr()),
+                        "hl_tf32_split_batch")
+            self.ready = torch.cuda.Event()
+            self.ready.record(self.stream)       # every GEMM call site waits for it (`get`), which also rejoins
+        return self                              # the plan's stream into a graph capture
+
+    def __exit__(self, *a):
+        global _PLAN
+        _PLAN = None
+        if self.entries and (self._table is None or self._n_entries != len(self.entries)):
+            if not torch.cuda.is_current_stream_capturing():       # the H2D copy of the table cannot be captured
+                self._build_table(next(iter(self.entries.values()))[1].device)
+
+    def get(self, key):
+        ent = self.entries.get(key)
+        if ent is None or self.ready is None:
+            return None
+        torch.cuda.current_stream().wait_event(self.ready)
+        return ent[1], ent[2]
+
+
+_PLAN = None
+
+
+def _split_weights(key, views, shape, launches, zero):
+    """hi / lo buffers of `shape` for a split request: from the active plan if it has them, else split now on the
+    current stream (and hand the buffers to the plan, if one is recording).  `launches`: callables (hi, lo) ->
+    hl_tf32_split argument tuple (without the stream)."""
+    plan = _PLAN
+    if plan is not None:
+        hit = plan.get(key)
+        if hit is not None:
+            return hit
+    dev = views[0].device
+    alloc = torch.zeros if zero else torch.empty
+    hi, lo = alloc(shape, dtype=torch.float32, device=dev), alloc(shape, dtype=torch.float32, device=dev)
+    args = [mk(hi, lo) for mk in launches]
+    L, st = N.lib(), N.stream_ptr()
+    for a in args:
+        N.check(L.hl_tf32_split(*a, st), "hl_tf32_split")
+    if plan is not None and key not in plan.entries and not torch.cuda.is_current_stream_capturing():
+        plan.entries[key] = (views, hi, lo, args)      # hi / lo allocated inside a capture belong to the graph's pool
+    return hi, lo
+
+
+def _view_key(t):
+    return (t.data_ptr(), tuple(t.shape), tuple(t.stride()))
+
+
 def dense(a, w, bias=None, out=None, accumulate=False, transpose_w=False):
     """out (=|+=) a @ w.T (+ bias)   [transpose_w: a @ w].  fp32-accurate tcgen05 GEMM (3xTF32 split) when the
     shape allows (N % 16 == 0, 16-byte aligned rows), else the cuBLAS fp32 GEMM."""
@@ -149,12 +243,11 @@ def dense(a, w, bias=None, out=None, accumulate=False, transpose_w=False):
     if _GEMM_MODE["tensor"] and M > 0 and n_out % 16 == 0 and a.stride(1) == 1 and a.stride(0) % 4 == 0 \
             and a.data_ptr() % 16 == 0 and K % 4 == 0 and out.stride(1) == 1:
         kp = K
-        hi = torch.empty((n_out, kp), dtype=torch.float32, device=a.device)
-        lo = torch.empty((n_out, kp), dtype=torch.float32, device=a.device)
         # w is [n_out, K] (or [K, n_out] when transpose_w): split into tf32-exact hi and remainder lo, [n_out, K]
         rows, cols = (K, n_out) if transpose_w else (n_out, K)
-        N.check(L.hl_tf32_split(w.data_ptr(), w.stride(0), rows, cols, 1 if transpose_w else 0,
-                                hi.data_ptr(), lo.data_ptr(), kp, N.stream_ptr()), "hl_tf32_split")
+        tr = 1 if transpose_w else 0
+        hi, lo = _split_weights(("1", tr) + _view_key(w), (w,), (n_out, kp),
+                                [lambda h, l: (w.data_ptr(), w.stride(0), rows, cols, tr, h.data_ptr(), l.data_ptr(), kp)], False)
         rc = L.hl_gemm_tf32x3(a.data_ptr(), a.stride(0), hi.data_ptr(), lo.data_ptr(), kp, M, n_out, K, N.ptr(bias),
                               out.data_ptr(), out.stride(0), 1 if accumulate else 0, N.stream_ptr())
         if rc == 0:
@@ -184,13 +277,12 @@ def dense2(a1, w1, a2, w2, bias=None, out=None, accumulate=False):
     if ok:
         k1p = (k1 + 31) // 32 * 32
         kt = k1p + k2
-        alloc = torch.empty if k1p == k1 else torch.zeros          # pad columns k1..k1p of the packed weights must be 0
-        hi = alloc((n_out, kt), dtype=torch.float32, device=a1.device)
-        lo = alloc((n_out, kt), dtype=torch.float32, device=a1.device)
         st = N.stream_ptr()
-        N.check(L.hl_tf32_split(w1.data_ptr(), w1.stride(0), n_out, k1, 0, hi.data_ptr(), lo.data_ptr(), kt, st), "hl_tf32_split")
-        N.check(L.hl_tf32_split(w2.data_ptr(), w2.stride(0), n_out, k2, 0, hi[:, k1p:].data_ptr(), lo[:, k1p:].data_ptr(), kt, st),
-                "hl_tf32_split")
+        # packed [w1 | pad | w2] along K; the pad columns k1..k1p of the packed weights must be 0
+        hi, lo = _split_weights(("2",) + _view_key(w1) + _view_key(w2), (w1, w2), (n_out, kt),
+                                [lambda h, l: (w1.data_ptr(), w1.stride(0), n_out, k1, 0, h.data_ptr(), l.data_ptr(), kt),
+                                 lambda h, l: (w2.data_ptr(), w2.stride(0), n_out, k2, 0, h[:, k1p:].data_ptr(), l[:, k1p:].data_ptr(), kt)],
+                                k1p != k1)
         if out is None:
             out = torch.empty((M, n_out), dtype=torch.float32, device=a1.device)
             accumulate = False

@@ -15,7 +15,7 @@ from types import SimpleNamespace
 import torch
 
 from . import lanes
-from .functional import accumulate_into_grads
+from .functional import accumulate_into_grads, WeightSplitPlan
 from .simplex import clear_caches
 
 _PAD_KEYS = ("x_t", "x_s", "y", "edge_index", "edge_index_t", "edge_index_s", "edge_weight_t", "edge_weight_s",
@@ -144,6 +144,7 @@ class GraphedTrainStep:
         self.device = device
         self.batch = StaticBatch(proto_batch, device)
         self.loss = torch.zeros((), device=device)
+        self.split_plan = WeightSplitPlan() if warmup >= 2 else None     # recorded by the first warm-up step
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
@@ -166,6 +167,12 @@ class GraphedTrainStep:
         clear_caches()
 
     def _fwd_bwd(self):
+        if self.split_plan is None:
+            return self._fwd_bwd_body()
+        with self.split_plan:              # all weight hi / lo splits in one launch on a side branch
+            return self._fwd_bwd_body()
+
+    def _fwd_bwd_body(self):
         clear_caches()                     # the static COO buffers change content between replays
         self.bucket.zero()
         if self.loss_fn:

@@ -282,6 +282,21 @@ int hl_greedy_matching(const int32_t* node_ptr, int32_t n_graphs, const int32_t*
  * -------------------------------------------------------------------------------------------- */
 int hl_tf32_split(const float* src, int64_t ld_src, int32_t rows, int32_t cols, int transpose,
                   float* hi, float* lo, int64_t ld_out, hl_stream_t stream);
+/* The same split for a table of weight views in ONE launch (all weights of a model at the top of a training step,
+ * off the critical chain of the GEMMs that consume them).  `table`: DEVICE array of n_entries descriptors;
+ * max_elements = max rows*cols over the table (sizes the grid). */
+typedef struct hl_split_desc {
+  const float* src;   /* [rows, cols], row pitch ld_src */
+  float* hi;          /* [rows, cols] (or [cols, rows] when transpose), row pitch ld_out */
+  float* lo;
+  int64_t ld_src;
+  int64_t ld_out;
+  int32_t rows;
+  int32_t cols;
+  int32_t transpose;
+  int32_t reserved;
+} hl_split_desc;
+int hl_tf32_split_batch(const hl_split_desc* table, int32_t n_entries, int64_t max_elements, hl_stream_t stream);
 int hl_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb,
                    int32_t M, int32_t N, int32_t K, const float* bias, float* C, int64_t ldc,
                    int accumulate, hl_stream_t stream);

@@ -170,3 +170,34 @@ def test_graphed_two_level_lanes_bit_identical():
         results.append((losses, [p.detach().clone() for p in m.parameters()], list(m.named_parameters())))
         H.enable_lanes(False)
     _check_graphed(results)
+
+
+def test_weight_split_plan_replays_bit_identical():
+    """functional.WeightSplitPlan: recorded weight splits re-issued in one launch give the same GEMM results, bit
+    for bit, as splitting at the call site -- also after the weights were updated in place."""
+    from hlhgat_b200 import functional as F_hl
+    torch.manual_seed(0)
+    a = torch.randn(1000, 96, device=DEV)
+    a2 = torch.randn(1000, 40, device=DEV)          # 40 % 32 != 0: padded packing of [w1 | w2]
+    g = torch.randn(1000, 64, device=DEV)
+    w = torch.randn(64, 96, device=DEV) * 0.1
+    w1 = torch.randn(64, 40, device=DEV) * 0.1
+    w2 = torch.randn(64, 96, device=DEV) * 0.1
+
+    def run():
+        return (F_hl.dense(a, w), F_hl.dense(g, w, transpose_w=True), F_hl.dense2(a2, w1, a, w2),
+                F_hl.dense2(a[:, :64], w[:, :64], a[:, 64:], w[:, 64:]))
+
+    plan = F_hl.WeightSplitPlan()
+    with plan:
+        first = run()                                # records
+    assert len(plan.entries) == 4 and plan._table_len == 6
+    for t in (w, w1, w2):
+        t.mul_(1.7).add_(0.01)
+    ref = run()                                      # no plan: split at the call site
+    with plan:
+        got = run()                                  # replay: one hl_tf32_split_batch launch
+        assert plan.ready is not None
+    torch.cuda.synchronize()
+    for x, y, z in zip(got, ref, first):
+        assert torch.equal(x, y) and not torch.equal(x, z)
