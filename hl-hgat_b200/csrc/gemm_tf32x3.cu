@@ -475,33 +475,52 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
   return HL_OK;
 }
 
-// dw (=|+=) sum over the row splits: 8 lanes per output element (k = lane, lane + 8, ...), fixed shuffle tree
+// dw (=|+=) sum over the row splits: 8 lanes per group of 4 consecutive output elements (one float4 per split
+// plane and lane: k = lane, lane + 8, ...; whole 32-byte sectors of every plane), fixed shuffle tree -> deterministic
 __global__ void __launch_bounds__(256)
 gm_split_reduce_kernel(const float* __restrict__ partial, int32_t splits, int64_t split_stride, int32_t fo,
                        int32_t fi, float* __restrict__ dw, int64_t ld_dw, int accumulate) {
-  const int64_t n = (int64_t)fo * fi;
+  const int64_t n4 = ((int64_t)fo * fi) >> 2;                      // fi % 32 == 0: rows never straddle a float4
   const int sub = threadIdx.x & 7;
-  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < ((n + 31) & ~(int64_t)31);
+  const bool vec_out = (ld_dw % 4 == 0) && ((reinterpret_cast<uintptr_t>(dw) & 15) == 0);
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < ((n4 + 3) & ~(int64_t)3);
        i += ((int64_t)gridDim.x * blockDim.x) >> 3) {
-    float s = 0.f;
-    if (i < n) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n4) {
+      const float4* p = reinterpret_cast<const float4*>(partial) + i;
+      const int64_t stride4 = split_stride >> 2;
       int k = sub;
       for (; k + 24 < splits; k += 32) {
-        float v[4];
+        float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __ldg(partial + (int64_t)(k + 8 * u) * split_stride + i);
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(p + (int64_t)(k + 8 * u) * stride4);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) s += v[u];
+        for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
       }
-      for (; k < splits; k += 8) s += __ldg(partial + (int64_t)k * split_stride + i);
+      for (; k < splits; k += 8) {
+        const float4 v = __ldg(p + (int64_t)k * stride4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
     }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (sub == 0 && i < n) {
-      const int64_t o = i / fi, c = i - o * fi;
-      float* p = dw + o * ld_dw + c;
-      *p = accumulate ? *p + s : s;
+#pragma unroll
+    for (int m = 1; m < 8; m <<= 1) {
+      s.x += __shfl_xor_sync(0xffffffffu, s.x, m);
+      s.y += __shfl_xor_sync(0xffffffffu, s.y, m);
+      s.z += __shfl_xor_sync(0xffffffffu, s.z, m);
+      s.w += __shfl_xor_sync(0xffffffffu, s.w, m);
+    }
+    if (sub == 0 && i < n4) {
+      const int64_t e = i << 2;
+      const int64_t o = e / fi, c = e - o * fi;
+      float* q = dw + o * ld_dw + c;
+      if (vec_out) {
+        float4* q4 = reinterpret_cast<float4*>(q);
+        if (accumulate) { const float4 t = *q4; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+        *q4 = s;
+      } else {
+        q[0] = accumulate ? q[0] + s.x : s.x; q[1] = accumulate ? q[1] + s.y : s.y;
+        q[2] = accumulate ? q[2] + s.z : s.z; q[3] = accumulate ? q[3] + s.w : s.w;
+      }
     }
   }
 }
@@ -560,7 +579,7 @@ extern "C" int hl_wgrad_tf32x3(const float* g, int64_t ld_g, const float* x, int
   gemm_tf32x3_kernel<1><<<grid, kGmThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
   HL_LAUNCH_CHECK("gemm_tf32x3_kernel<wgrad>");
   const int64_t n = (int64_t)fo * fi;
-  gm_split_reduce_kernel<<<(int)((n * 8 + 255) / 256), 256, 0, as_stream(stream)>>>(P.C, splits, P.split_stride, fo, fi, dw, ld_dw,
+  gm_split_reduce_kernel<<<(int)((n * 2 + 255) / 256), 256, 0, as_stream(stream)>>>(P.C, splits, P.split_stride, fo, fi, dw, ld_dw,
                                                                                accumulate);
   HL_LAUNCH_CHECK("gm_split_reduce_kernel");
   return HL_OK;

@@ -704,10 +704,13 @@ class _BnAct(torch.autograd.Function):
         ctx.params = (gamma, beta)
         ctx.save_for_backward(x, y, gamma, stats)
         ctx.mark_non_differentiable(stats)
+        ctx.set_materialize_grads(False)           # no zero-filled gradient tensor for `stats` on every backward
         return y, stats
 
     @staticmethod
     def backward(ctx, dy, _):
+        if dy is None:
+            return (None,) * 10
         x, y, gamma, stats = ctx.saved_tensors
         L = N.lib()
         R, F = x.shape
