@@ -333,12 +333,54 @@ def run_ours(args, world, rank, local):
         line["roofline"] = spmm_roofline(dev, batch_to(b0, dev), args.workload)
     except Exception as exc:  # pragma: no cover
         line["roofline"] = {"error": repr(exc)}
+    try:
+        line["roofline_dense"] = dense_roofline(dev, caps[0].nodes)
+    except Exception as exc:  # pragma: no cover
+        line["roofline_dense"] = {"error": repr(exc)}
     if world == 1 and not args.no_cpu_baseline:
         gps, ms_cpu, cores = cpu_reference_throughput(wl, 3, 1, wl.cpu_sample)
         line["cpu_baseline"] = {"value": gps, "unit": "graphs/s", "cores": cores, "kind": "port",
                                 "sample": f"3 training steps (1 warm-up) on {wl.cpu_sample}-graph batches of the same shape, same model, "
                                           f"{cores} torch threads; pure-torch restatement of the reference, not PyG"}
     print(json.dumps(line), file=_OUT, flush=True)
+
+
+def dense_roofline(dev, rows, iters=20):
+    """Second roofline leg (the dense Theta / MLP transform is the largest share of the step's kernel time): the
+    tcgen05 3xTF32 GEMM on the largest dense shape of the ZINC stack, [rows,1408] x [1408,256]^T (first MLP Linear of
+    the last NodeEdgeInt; A = 136 MB > L2).  fp32-equivalent FLOPs 2*M*N*K over the CUDA-event time; every
+    product costs three tf32 MMAs and tf32 runs at half the bf16 rate, so the tensor-pipe ceiling for this arithmetic
+    is bf16_peak / 6."""
+    from hlhgat_b200 import _native as N
+    L = N.lib()
+    M, Nn, K = int(rows), 256, 1408
+    a = torch.randn(M, K, device=dev)
+    w = torch.randn(Nn, K, device=dev) * 0.05
+    hi, lo, c = torch.empty_like(w), torch.empty_like(w), torch.empty(M, Nn, device=dev)
+    N.check(L.hl_tf32_split(w.data_ptr(), K, Nn, K, 0, hi.data_ptr(), lo.data_ptr(), K, N.stream_ptr()), "hl_tf32_split")
+
+    def launch():
+        rc = L.hl_gemm_tf32x3(a.data_ptr(), K, hi.data_ptr(), lo.data_ptr(), K, M, Nn, K, None, c.data_ptr(), Nn, 0, N.stream_ptr())
+        if rc != 0:
+            raise RuntimeError(f"hl_gemm_tf32x3 returned {rc}")
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for e0, e1 in evs:
+        e0.record()
+        launch()
+        e1.record()
+    torch.cuda.synchronize()
+    ms = statistics.mean(e0.elapsed_time(e1) for e0, e1 in evs)
+    pk, kind = peaks()
+    ach = 2.0 * M * Nn * K / (ms * 1e-3) / 1e12
+    peak = pk["bf16_tflops"] / 6.0
+    err = float((c[:256].double() - a[:256].double() @ w.double().t()).abs().max() / (a[:256].double() @ w.double().t()).abs().max())
+    return {"bound": "tensor", "kernel": "gemm_tf32x3_kernel<0> (tcgen05.mma kind::tf32, 3 MMAs per product, fp32 TMEM accumulator)",
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "peak_kind": f"{kind} dense bf16 {pk['bf16_tflops']:.0f} TFLOP/s / 2 (tf32 rate) / 3 (MMAs per fp32-accurate product)",
+            "us_per_launch": ms * 1e3, "shape": [M, Nn, K], "max_rel_err_vs_fp64": err, "traffic": None}
 
 
 def _claim_stdout():
