@@ -86,6 +86,10 @@ _SIGNATURES = {
     "hl_bn_act_fwd": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _vp, _i64, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _sz, _vp]),
     "hl_bn_act_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32,
                                 _vp, _i64, _vp, _vp, C.c_int, _vp, _vp, _sz, _vp]),
+    "hl_bn_stats": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "hl_bn_apply": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _f32, _f32, _vp, _i64, _vp, _vp]),
+    "hl_bn_bwd_sums": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _f32, _f32, _vp, _vp, _vp, _sz, _vp]),
+    "hl_bn_bwd_apply": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _i64, _vp, _vp]),
 }
 
 _lib = None

@@ -220,11 +220,11 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ y, int64_t ld_y,
                     const float* __restrict__ dy, int64_t ld_dy, int32_t nrows, const int32_t* __restrict__ nvalid, int32_t width,
                     const float* __restrict__ gamma, const float* __restrict__ stats, const float* __restrict__ sums,
-                    float eps, float slope, float* __restrict__ dx, int64_t ld_dx) {
+                    float eps, float slope, float* __restrict__ dx, int64_t ld_dx, const float* __restrict__ inv_count) {
   const int chunks = width / V;
   const int64_t total = (int64_t)nrows * chunks;
   const int32_t nv = nvalid ? min(__ldg(nvalid), nrows) : nrows;
-  const float inv_n = 1.f / (float)max(nv, 1);
+  const float inv_n = inv_count ? __ldg(inv_count) : 1.f / (float)max(nv, 1);   // inv_count: 1 / rows over ALL ranks (SyncBN)
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(idx / chunks);
@@ -321,9 +321,90 @@ extern "C" int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64
   bn_bwd_final_kernel<<<(width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st>>>(partial, nblk, width, sums, dgamma, dbeta, accumulate_param_grads);
   HL_LAUNCH_CHECK("bn_bwd_final_kernel");
   const int g = ew_grid((int64_t)nrows * (width / V));
-  if (V == 4) bn_bwd_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx);
-  else if (V == 2) bn_bwd_apply_kernel<2><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx);
-  else bn_bwd_apply_kernel<1><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx);
+  if (V == 4) bn_bwd_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
+  else if (V == 2) bn_bwd_apply_kernel<2><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
+  else bn_bwd_apply_kernel<1><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
+  HL_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  return HL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same kernels as separate phases, for BatchNorm statistics synchronised across data-parallel ranks: the caller
+// exchanges the per-rank statistics (forward) / column sums (backward) between the reduction and the apply phase.
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int hl_bn_stats(const float* x, int64_t ld_x, int32_t nrows, int32_t width, float* stats,
+                           const int32_t* nvalid, void* workspace, size_t workspace_bytes, hl_stream_t stream) {
+  using namespace hl;
+  if (nrows < 1 || width < 1 || !x || !stats) return HL_ERR_INVALID;
+  if (!workspace || workspace_bytes < hl_bn_workspace(nrows, width)) return HL_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  double* partial = reinterpret_cast<double*>(workspace);
+  const int V = vec_for(x, ld_x, width, 4);
+  const int nblk = bn_row_blocks(nrows);
+  dim3 grid(nblk, (width + 32 * V - 1) / (32 * V));
+  if (V == 4) bn_stats_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
+  else if (V == 2) bn_stats_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
+  else bn_stats_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
+  HL_LAUNCH_CHECK("bn_stats_partial_kernel");
+  bn_stats_final_kernel<<<(width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st>>>(partial, nblk, x, nrows, nvalid, width, stats,
+                                                                    nullptr, nullptr, 0.f, nullptr);
+  HL_LAUNCH_CHECK("bn_stats_final_kernel");
+  return HL_OK;
+}
+
+extern "C" int hl_bn_apply(const float* x, int64_t ld_x, int32_t nrows, int32_t width, const float* gamma,
+                           const float* beta, const float* stats, float eps, float slope, float* y, int64_t ld_y,
+                           const int32_t* nvalid, hl_stream_t stream) {
+  using namespace hl;
+  if (nrows < 1 || width < 1 || !x || !y || !stats) return HL_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  int V = vec_for(x, ld_x, width, 4);
+  V = min(V, vec_for(y, ld_y, width, V));
+  const int g = ew_grid((int64_t)nrows * (width / V));
+  if (V == 4) bn_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else if (V == 2) bn_apply_kernel<2><<<g, 256, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else bn_apply_kernel<1><<<g, 256, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  HL_LAUNCH_CHECK("bn_apply_kernel");
+  return HL_OK;
+}
+
+extern "C" int hl_bn_bwd_sums(const float* x, int64_t ld_x, const float* y, int64_t ld_y, const float* dy, int64_t ld_dy,
+                              int32_t nrows, int32_t width, const float* stats, float eps, float slope, float* sums,
+                              const int32_t* nvalid, void* workspace, size_t workspace_bytes, hl_stream_t stream) {
+  using namespace hl;
+  if (nrows < 1 || width < 1 || !x || !y || !dy || !stats || !sums) return HL_ERR_INVALID;
+  if (!workspace || workspace_bytes < hl_bn_workspace(nrows, width)) return HL_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  const int nblk = bn_row_blocks(nrows);
+  double* partial = reinterpret_cast<double*>(workspace);
+  int V = vec_for(x, ld_x, width, 4);
+  V = min(V, vec_for(y, ld_y, width, V));
+  V = min(V, vec_for(dy, ld_dy, width, V));
+  dim3 grid(nblk, (width + 32 * V - 1) / (32 * V));
+  if (V == 4) bn_bwd_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
+  else if (V == 2) bn_bwd_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
+  else bn_bwd_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
+  HL_LAUNCH_CHECK("bn_bwd_partial_kernel");
+  bn_bwd_final_kernel<<<(width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st>>>(partial, nblk, width, sums, nullptr, nullptr, 0);
+  HL_LAUNCH_CHECK("bn_bwd_final_kernel");
+  return HL_OK;
+}
+
+extern "C" int hl_bn_bwd_apply(const float* x, int64_t ld_x, const float* y, int64_t ld_y, const float* dy, int64_t ld_dy,
+                               int32_t nrows, int32_t width, const float* gamma, const float* stats, const float* sums,
+                               const float* inv_count, float eps, float slope, float* dx, int64_t ld_dx,
+                               const int32_t* nvalid, hl_stream_t stream) {
+  using namespace hl;
+  if (nrows < 1 || width < 1 || !x || !y || !dy || !dx || !stats || !sums) return HL_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  int V = vec_for(x, ld_x, width, 4);
+  V = min(V, vec_for(y, ld_y, width, V));
+  V = min(V, vec_for(dy, ld_dy, width, V));
+  V = min(V, vec_for(dx, ld_dx, width, V));
+  const int g = ew_grid((int64_t)nrows * (width / V));
+  if (V == 4) bn_bwd_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
+  else if (V == 2) bn_bwd_apply_kernel<2><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
+  else bn_bwd_apply_kernel<1><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
   HL_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return HL_OK;
 }

@@ -731,6 +731,83 @@ class _BnAct(torch.autograd.Function):
         return dx, dgamma, dbeta, None, None, None, None, None, None, None
 
 
+class _SyncBnAct(torch.autograd.Function):
+    """Training BatchNorm + (leaky) ReLU with statistics over all ranks of a process group: the kernels of
+    `_BnAct` run as separate phases (hl_bn_stats / hl_bn_apply, hl_bn_bwd_sums / hl_bn_bwd_apply) with one small
+    exchange between them (parallel.combine_bn_stats / reduce_bn_sums).  dgamma / dbeta are this rank's own
+    column sums -- the gradient all-reduce averages them like every other parameter gradient."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, slope, nvalid, group):
+        from . import parallel as P
+        N.require_cuda_f32(x, gamma, beta)
+        L = N.lib()
+        x, ldx = N.row_major(x)
+        R, F = x.shape
+        y = torch.empty((R, F), dtype=torch.float32, device=x.device)
+        local = torch.empty(2 * F, dtype=torch.float32, device=x.device)
+        nb = L.hl_bn_workspace(R, F)
+        ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+        N.check(L.hl_bn_stats(x.data_ptr(), ldx, R, F, local.data_ptr(), N.ptr(nvalid), ws.data_ptr(), nb, N.stream_ptr()),
+                "hl_bn_stats")
+        count = nvalid.to(torch.float32) if nvalid is not None else torch.full((1,), float(R), device=x.device)
+        stats, total = P.combine_bn_stats(local, count, group)
+        N.check(L.hl_bn_apply(x.data_ptr(), ldx, R, F, N.ptr(gamma), N.ptr(beta), stats.data_ptr(), eps, slope,
+                              y.data_ptr(), y.stride(0), N.ptr(nvalid), N.stream_ptr()), "hl_bn_apply")
+        ctx.eps, ctx.slope, ctx.nvalid, ctx.group = eps, slope, nvalid, group
+        ctx.params = (gamma, beta)
+        inv_total = (1.0 / total.clamp(min=1.0)).reshape(1).contiguous()
+        ctx.save_for_backward(x, y, gamma, stats, inv_total)
+        ctx.mark_non_differentiable(stats, total)
+        ctx.set_materialize_grads(False)
+        return y, stats, total
+
+    @staticmethod
+    def backward(ctx, dy, _s, _t):
+        if dy is None:
+            return (None,) * 7
+        from . import parallel as P
+        x, y, gamma, stats, inv_total = ctx.saved_tensors
+        L = N.lib()
+        R, F = x.shape
+        dy, lddy = N.row_major(dy)
+        dx = torch.empty((R, F), dtype=torch.float32, device=x.device)
+        sums = torch.empty(2 * F, dtype=torch.float32, device=x.device)
+        nb = L.hl_bn_workspace(R, F)
+        ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+        N.check(L.hl_bn_bwd_sums(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), dy.data_ptr(), lddy, R, F,
+                                 stats.data_ptr(), ctx.eps, ctx.slope, sums.data_ptr(), N.ptr(ctx.nvalid), ws.data_ptr(), nb,
+                                 N.stream_ptr()), "hl_bn_bwd_sums")
+        gsums = P.reduce_bn_sums(sums, ctx.group)
+        N.check(L.hl_bn_bwd_apply(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), dy.data_ptr(), lddy, R, F,
+                                  N.ptr(gamma), stats.data_ptr(), gsums.data_ptr(), inv_total.data_ptr(), ctx.eps, ctx.slope,
+                                  dx.data_ptr(), dx.stride(0), N.ptr(ctx.nvalid), N.stream_ptr()), "hl_bn_bwd_apply")
+        dbeta, dgamma = sums[:F], sums[F:]
+        tg, tb = _grad_target(ctx.params[0]), _grad_target(ctx.params[1])
+        if tg is not None and tb is not None:
+            tg.add_(dgamma)
+            tb.add_(dbeta)
+            dgamma = dbeta = None
+        return dx, dgamma, dbeta, None, None, None, None
+
+
+def bn_act_train_synced(x, gamma, beta, group, eps=1e-5, slope=0.0, nvalid=None, running_mean=None, running_var=None,
+                        momentum=0.1, counter=None):
+    """`bn_act_train` with batch statistics over all ranks of `group`; returns (y, stats[2F]).  Running statistics
+    follow nn.SyncBatchNorm: global mean, unbiased global variance (N - 1 over all ranks)."""
+    y, stats, total = _SyncBnAct.apply(x, gamma, beta, float(eps), float(slope), nvalid, group)
+    if running_mean is not None:
+        f = running_mean.numel()
+        with torch.no_grad():
+            unbias = total / (total - 1.0).clamp(min=1.0)
+            running_mean.mul_(1.0 - momentum).add_(stats[:f] * momentum)
+            running_var.mul_(1.0 - momentum).add_(stats[f:] * (unbias * momentum))
+    if counter is not None:
+        with torch.no_grad():
+            counter += 1
+    return y, stats
+
+
 def bn_act_train(x, gamma, beta, eps=1e-5, slope=0.0, nvalid=None, running_mean=None, running_var=None, momentum=0.1,
                  counter=None):
     """Training-mode BatchNorm1d over rows + (leaky) ReLU; returns (y, stats[2F] = mean | biased var).

@@ -14,6 +14,7 @@ from torch.nn import Parameter
 
 from .. import functional as F_hl
 from .. import lanes as _lanes
+from .. import parallel as _parallel
 from .. import _native as N
 from ..simplex import operator_for, incidence_for, CsrOperator, Incidence
 
@@ -265,9 +266,15 @@ def _bn_relu(bn, x, slope=0.0, nvalid=None):
             m, counter = 1.0 / float(bn.num_batches_tracked), None
         else:
             m = bn.momentum                   # the counter is incremented inside the statistics kernel
-        y, _ = F_hl.bn_act_train(x, bn.weight, bn.bias, bn.eps, slope, nvalid, bn.running_mean, bn.running_var, m, counter)
+        rm, rv = bn.running_mean, bn.running_var
     else:
-        y, _ = F_hl.bn_act_train(x, bn.weight, bn.bias, bn.eps, slope, nvalid)
+        rm = rv = counter = None
+        m = 0.1
+    group = _parallel.sync_batchnorm_group()
+    if group is not False:                    # opt-in: statistics over all data-parallel ranks (parallel.enable_sync_batchnorm)
+        y, _ = F_hl.bn_act_train_synced(x, bn.weight, bn.bias, group, bn.eps, slope, nvalid, rm, rv, m, counter)
+    else:
+        y, _ = F_hl.bn_act_train(x, bn.weight, bn.bias, bn.eps, slope, nvalid, rm, rv, m, counter)
     return y
 
 

@@ -45,3 +45,51 @@ def broadcast_parameters(module, src=0, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         for t in list(module.parameters()) + list(module.buffers()):
             dist.broadcast(t.data, src, group=group)
+
+
+# ---------------------------------------------------------------------------------------------
+# BatchNorm statistics over all ranks (caveat 1).  Plain data parallelism normalises with
+# per-rank statistics (what DDP does; the default here); the reference trains the whole batch on one GPU, so a
+# run that must match a single-GPU run of the GLOBAL batch needs these two exchanges per BatchNorm layer.
+# ---------------------------------------------------------------------------------------------
+_SYNC_BN = {"group": None, "enabled": False}
+
+
+def enable_sync_batchnorm(flag=True, group=None):
+    """Opt in: every training-mode BatchNorm of the module layer (lib/Hodge_Cheb_Conv._bn_relu) uses statistics
+    over all ranks of `group` (default: the world)."""
+    _SYNC_BN["enabled"], _SYNC_BN["group"] = bool(flag), group
+
+
+def sync_batchnorm_group():
+    """The process group to synchronise BatchNorm over, or False when synchronisation is off / pointless."""
+    if not _SYNC_BN["enabled"] or not (dist.is_available() and dist.is_initialized()):
+        return False
+    if dist.get_world_size(_SYNC_BN["group"]) < 2:
+        return False
+    return _SYNC_BN["group"]
+
+
+def combine_bn_stats(local_stats, local_count, group=None):
+    """Global (mean | biased variance) [2F] and row count from every rank's own: all-gather of [count, mean, var]
+    (2F + 1 floats per rank), merged in fp64 -- mean = sum n_r m_r / N, var = sum n_r (v_r + (m_r - mean)^2) / N
+    (no E[x^2] - mean^2 cancellation).  `local_count`: 0-dim / 1-element tensor on the same device."""
+    f = local_stats.numel() // 2
+    mine = torch.cat([local_count.reshape(1).to(local_stats.dtype), local_stats.reshape(-1)])
+    world = dist.get_world_size(group)
+    allr = torch.empty(world * (2 * f + 1), dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(allr, mine.contiguous(), group=group)
+    allr = allr.view(world, 2 * f + 1).double()
+    n, m, v = allr[:, :1], allr[:, 1:f + 1], allr[:, f + 1:]
+    total = n.sum()
+    denom = total.clamp(min=1.0)
+    mean = (n * m).sum(0) / denom
+    var = (n * (v + (m - mean) ** 2)).sum(0) / denom
+    return torch.cat([mean, var]).to(local_stats.dtype), total.to(local_stats.dtype)
+
+
+def reduce_bn_sums(local_sums, group=None):
+    """Column sums of dz and dz * xhat over all ranks (the per-rank ones stay this rank's dbeta / dgamma)."""
+    out = local_sums.clone()
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out

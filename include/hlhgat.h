@@ -258,6 +258,26 @@ int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64_t ld_y,
                   int accumulate_param_grads /* dgamma / dbeta: 0 = overwrite, 1 = += (fused gradient accumulation) */,
                   const int32_t* nvalid, void* workspace, size_t workspace_bytes, hl_stream_t stream);
 
+/* The same BatchNorm as separate phases, for statistics synchronised across data-parallel ranks (SURVEY section 8e,
+ * caveat 1: the reference trains the whole batch on one GPU, so matching a single-GPU run of the GLOBAL batch needs
+ * batch statistics over all ranks).  Forward: hl_bn_stats (per-rank mean | biased variance) -> the caller combines
+ * the ranks' statistics -> hl_bn_apply with the global ones.  Backward: hl_bn_bwd_sums (per-rank column sums of
+ * dz and dz * xhat, dz = dy * act'(y); these are also this rank's dbeta / dgamma) -> the caller sums them over the
+ * ranks -> hl_bn_bwd_apply with the global sums and *inv_count = 1 / (rows over all ranks) (device scalar; NULL =
+ * this rank's own row count). */
+int hl_bn_stats(const float* x, int64_t ld_x, int32_t nrows, int32_t width, float* stats /* [2*width] */,
+                const int32_t* nvalid, void* workspace, size_t workspace_bytes, hl_stream_t stream);
+int hl_bn_apply(const float* x, int64_t ld_x, int32_t nrows, int32_t width, const float* gamma, const float* beta,
+                const float* stats, float eps, float slope, float* y, int64_t ld_y, const int32_t* nvalid,
+                hl_stream_t stream);
+int hl_bn_bwd_sums(const float* x, int64_t ld_x, const float* y, int64_t ld_y, const float* dy, int64_t ld_dy,
+                   int32_t nrows, int32_t width, const float* stats, float eps, float slope, float* sums /* [2*width] */,
+                   const int32_t* nvalid, void* workspace, size_t workspace_bytes, hl_stream_t stream);
+int hl_bn_bwd_apply(const float* x, int64_t ld_x, const float* y, int64_t ld_y, const float* dy, int64_t ld_dy,
+                    int32_t nrows, int32_t width, const float* gamma, const float* stats, const float* sums,
+                    const float* inv_count /* device, nullable */, float eps, float slope, float* dx, int64_t ld_dx,
+                    const int32_t* nvalid, hl_stream_t stream);
+
 /* --------------------------------------------------------------------------------------------
  * Greedy heavy-edge matching for multi-level graph coarsening, one warp per graph of the mini-batch.
  * Nodes are visited in id order; an unmatched node u pairs with its unmatched neighbour of largest edge_weight

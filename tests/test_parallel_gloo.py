@@ -72,3 +72,57 @@ def test_shard_graphs_balances_cost():
     loads = [sum(costs[i] for i in p) for p in parts]
     assert abs(loads[0] - loads[1]) <= 3
     assert shard_graphs([5, 4], 4) == [[0], [1], [], []]
+
+
+# ---------------------------------------------------------------------------------------------
+# BatchNorm statistics over all ranks (parallel.combine_bn_stats / reduce_bn_sums): the exchange and the merge
+# formulas, world size 2 on gloo, against torch's batch_norm + autograd on the concatenated batch.  The per-rank
+# phases (what hl_bn_stats / hl_bn_bwd_sums / hl_bn_bwd_apply compute on the GPU) are restated in torch here.
+# ---------------------------------------------------------------------------------------------
+def _syncbn_worker(rank, world, init_file, out_dir):
+    sys.path.insert(0, ROOT)
+    import hlhgat_b200  # noqa: F401
+    from hlhgat_b200 import parallel as P
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(5)
+    x_all = torch.randn(37, 6, generator=g) * 3 + 100.0          # large mean: E[x^2] - mean^2 would cancel in fp32
+    dy_all = torch.randn(37, 6, generator=g)
+    gamma = torch.rand(6, generator=g) + 0.5
+    rows = slice(0, 23) if rank == 0 else slice(23, 37)          # unequal shards
+    x, dy = x_all[rows], dy_all[rows]
+    eps, slope = 1e-5, 0.1
+    local = torch.cat([x.mean(0), x.var(0, unbiased=False)])
+    stats, total = P.combine_bn_stats(local, torch.tensor([float(x.shape[0])]))
+    mean, rstd = stats[:6], (stats[6:] + eps).rsqrt()
+    xhat = (x - mean) * rstd
+    z = xhat * gamma
+    y = torch.where(z > 0, z, z * slope)
+    dz = torch.where(y > 0, dy, dy * slope)
+    sums = torch.cat([dz.sum(0), (dz * xhat).sum(0)])
+    gs = P.reduce_bn_sums(sums)
+    dx = gamma * rstd * (dz - gs[:6] / total - xhat * gs[6:] / total)
+    torch.save({"stats": stats, "total": total, "y": y, "dx": dx, "dgamma": sums[6:], "dbeta": sums[:6]},
+               os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sync_batchnorm_exchange_world2_gloo():
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_syncbn_worker, args=(2, os.path.join(d, "init"), d), nprocs=2, join=True)
+        r = [torch.load(os.path.join(d, f"r{k}.pt")) for k in range(2)]
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(37, 6, generator=g) * 3 + 100.0).requires_grad_(True)
+    dy = torch.randn(37, 6, generator=g)
+    gamma = (torch.rand(6, generator=g) + 0.5).requires_grad_(True)
+    beta = torch.zeros(6, requires_grad=True)
+    y = torch.nn.functional.leaky_relu(torch.nn.functional.batch_norm(x, None, None, gamma, beta, True, 0.0, 1e-5), 0.1)
+    dx, dgamma, dbeta = torch.autograd.grad(y, (x, gamma, beta), dy)
+    assert float(r[0]["total"]) == 37.0
+    assert torch.equal(r[0]["stats"], r[1]["stats"])
+    assert torch.allclose(r[0]["stats"][:6], x.detach().mean(0), rtol=1e-6)
+    assert torch.allclose(r[0]["stats"][6:], x.detach().var(0, unbiased=False), rtol=1e-4)
+    assert torch.allclose(torch.cat([r[0]["y"], r[1]["y"]]), y.detach(), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(torch.cat([r[0]["dx"], r[1]["dx"]]), dx, rtol=1e-3, atol=1e-5)
+    assert torch.allclose(r[0]["dgamma"] + r[1]["dgamma"], dgamma, rtol=1e-3, atol=1e-5)   # summed by the gradient all-reduce
+    assert torch.allclose(r[0]["dbeta"] + r[1]["dbeta"], dbeta, rtol=1e-4, atol=1e-5)
