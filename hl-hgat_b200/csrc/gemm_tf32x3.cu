@@ -67,6 +67,27 @@ __device__ __forceinline__ void gm_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (lane = tile row, 32-bit column = k index), B from shared memory
+__device__ __forceinline__ void gm_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void gm_tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void gm_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(gm_smem_u32(bar)) : "memory");
 }
@@ -106,12 +127,16 @@ struct GemmParams {
   int32_t kb_first;         // forward mode: k-blocks taken from the first A operand (the rest from the second)
   int32_t k_per_split;      // wgrad mode: rows of the contraction handled by one blockIdx.z (multiple of 32)
   int64_t split_stride;     // wgrad mode: elements between partial outputs of consecutive splits
+  int32_t tmem_a_col;       // TS variant: first TMEM column of the A_hi | A_lo slots (64 columns per ring stage)
 };
 
 // MODE 0: C = A[M,K] B[N,K]^T, both K-major, B pre-split (map_b = hi, map_b2 = lo).
 // MODE 1: weight gradient C[M,N] = G[R,M]^T X[R,N] over the row range of blockIdx.z: both operands MN-major
 //         (contraction over the rows), both split in the kernel; map_a = G, map_b = X, map_b2 unused.
-template <int MODE>
+// TS = 1 (MODE 0 only): the converter warps write A_hi / A_lo into TENSOR MEMORY (tcgen05.st) and the MMAs take A from
+//         there; a ring stage then holds only the raw A tile and B_hi / B_lo (48 KB instead of 64 KB at 128 columns:
+//         one more stage in flight) and the MMAs read half as many shared-memory bytes.
+template <int MODE, int TS = 0>
 __global__ void __launch_bounds__(kGmThreads)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                    const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_a2,
@@ -120,7 +145,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bn = P.bn, stages = P.stages;
   const uint32_t a_bytes = kGmBM * kGmBK * 4, b_bytes = (uint32_t)bn * kGmBK * 4;
-  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  const uint32_t stage_bytes = (TS ? 1 : 2) * a_bytes + 2 * b_bytes;
+  const uint32_t b_off = (TS ? 1 : 2) * a_bytes;                   // B_hi inside a stage (B_lo follows)
   unsigned char* base = gm_smem;                                   // 1024-byte aligned by the launch
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)stages * stage_bytes);
   uint64_t* full_bar = bars;                 // [stages]  TMA bytes landed
@@ -169,15 +195,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           // [A | A2] W^T: the second operand continues the contraction (B is packed [N, K1pad + K2])
           if (kb < P.kb_first) gm_tma_load_2d(st, &map_a, &full_bar[s], kb * kGmBK, m0);
           else gm_tma_load_2d(st, &map_a2, &full_bar[s], (kb - P.kb_first) * kGmBK, m0);
-          gm_tma_load_2d(st + 2 * a_bytes, &map_bhi, &full_bar[s], kb * kGmBK, n0);
-          gm_tma_load_2d(st + 2 * a_bytes + b_bytes, &map_blo, &full_bar[s], kb * kGmBK, n0);
+          gm_tma_load_2d(st + b_off, &map_bhi, &full_bar[s], kb * kGmBK, n0);
+          gm_tma_load_2d(st + b_off + b_bytes, &map_blo, &full_bar[s], kb * kGmBK, n0);
         } else {
           // stack of {32 cols, 32 rows} boxes: 4 for the 128 output rows (G columns), bn/32 for the output columns
           gm_mbar_arrive_expect_tx(&full_bar[s], a_bytes + b_bytes);
           const int row = k_begin + kb * kGmBK;
           for (int j = 0; j < kGmBM / 32; ++j) gm_tma_load_2d(st + j * 4096, &map_a, &full_bar[s], m0 + 32 * j, row);
           for (int j = 0; j < bn / 32; ++j)
-            gm_tma_load_2d(st + 2 * a_bytes + j * 4096, &map_bhi, &full_bar[s], n0 + 32 * j, row);
+            gm_tma_load_2d(st + b_off + j * 4096, &map_bhi, &full_bar[s], n0 + 32 * j, row);
         }
       }
     }
@@ -193,7 +219,20 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         gm_mbar_wait(&conv_bar[s], round & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = gm_smem_u32(base + (size_t)s * stage_bytes);
-        const uint32_t a_hi = st, a_lo = st + a_bytes, b_hi = st + 2 * a_bytes, b_lo = st + 2 * a_bytes + b_bytes;
+        const uint32_t a_hi = st, a_lo = st + a_bytes, b_hi = st + b_off, b_lo = st + b_off + b_bytes;
+        if (TS) {
+          const uint32_t ta_hi = tmem_base + (uint32_t)P.tmem_a_col + (uint32_t)s * 64u, ta_lo = ta_hi + 32u;
+#pragma unroll
+          for (int k = 0; k < kGmBK / 8; ++k) {
+            const uint32_t off = (uint32_t)k * 32u;
+            const uint64_t dbh = gm_desc_kmajor_sw128(b_hi + off), dbl = gm_desc_kmajor_sw128(b_lo + off);
+            gm_mma_tf32_ts(tmem_base, ta_lo + 8u * k, dbh, idesc, (kb | k) ? 1u : 0u);   // small terms first
+            gm_mma_tf32_ts(tmem_base, ta_hi + 8u * k, dbl, idesc, 1u);
+            gm_mma_tf32_ts(tmem_base, ta_hi + 8u * k, dbh, idesc, 1u);
+          }
+          gm_commit(&empty_bar[s]);
+          continue;
+        }
 #pragma unroll
         for (int k = 0; k < kGmBK / 8; ++k) {
           uint64_t dah, dal, dbh, dbl;
@@ -221,6 +260,32 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const int s = kb % stages;
       const uint32_t round = (uint32_t)(kb / stages);
       gm_mbar_wait(&full_bar[s], round & 1u);
+      if (TS) {
+        // thread = tile row = its own TMEM lane: un-swizzle the 128-byte row (16-byte chunk c sits at c ^ (row % 8)),
+        // split, and store hi | lo as 2 x 32 columns of the stage's TMEM slot
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
+        const unsigned char* arow = base + (size_t)s * stage_bytes + (size_t)r * 128;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 x = *reinterpret_cast<const float4*>(arow + ((c ^ (r & 7)) << 4));
+          const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint32_t h = __float_as_uint(xs[t]) & 0xffffe000u;
+            hi[4 * c + t] = h;
+            lo[4 * c + t] = __float_as_uint(xs[t] - __uint_as_float(h));
+          }
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)P.tmem_a_col + (uint32_t)s * 64u;
+        gm_tmem_st_x32(taddr, hi);
+        gm_tmem_st_x32(taddr + 32u, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        gm_mbar_arrive(&conv_bar[s]);
+        continue;
+      }
       float4* a = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes);
       float4* alo = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + a_bytes);
 #pragma unroll
@@ -236,8 +301,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         alo[idx] = l;                                               // hi stays implicit: kind::tf32 ignores the low 13 mantissa bits
       }
       if (MODE == 1) {
-        float4* b = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + 2 * a_bytes);
-        float4* blo = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + 2 * a_bytes + b_bytes);
+        float4* b = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + b_off);
+        float4* blo = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + b_off + b_bytes);
         for (int idx = ct; idx < (int)(b_bytes / 16); idx += kGmConvThreads) {
           const float4 x = b[idx];
           float4 h, l;
@@ -435,9 +500,10 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
   }
   const int ntiles = (N + max_bn - 1) / max_bn;
   const int bn = ((N + ntiles - 1) / ntiles + 15) / 16 * 16;
-  int tmem_cols = 32;
-  while (tmem_cols < bn) tmem_cols <<= 1;
-  const size_t stage_bytes = 2 * (size_t)kGmBM * kGmBK * 4 + 2 * (size_t)bn * kGmBK * 4;
+  // TS variant (A_hi / A_lo in tensor memory): HL_GEMM_TS=0 selects the all-shared-memory kernel
+  static int use_ts = -1;
+  if (use_ts < 0) { const char* e = getenv("HL_GEMM_TS"); use_ts = e ? atoi(e) : 1; }
+  const size_t stage_bytes = (use_ts ? 1 : 2) * (size_t)kGmBM * kGmBK * 4 + 2 * (size_t)bn * kGmBK * 4;
   int stages = (int)((200 * 1024) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 2) return 1;
@@ -449,10 +515,17 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
   static int co_resident = -1;
   if (co_resident < 0) { const char* e = getenv("HL_GEMM_CORESIDENT"); co_resident = e ? atoi(e) : 1; }
   const int64_t ctas = (int64_t)((M + kGmBM - 1) / kGmBM) * ntiles;
-  if (co_resident && ctas > 148 && ctas <= 2 * 148) {
-    const int s2 = (int)((108 * 1024) / stage_bytes);
+  const int tmem_a_col = (bn + 31) / 32 * 32;
+  if (co_resident && ctas > 148 && (ctas <= 2 * 148 || co_resident == 2)) {
+    int s2 = (int)((108 * 1024) / stage_bytes);
+    if (use_ts)                                              // two resident CTAs share the 512 TMEM columns
+      while (s2 >= 2 && tmem_a_col + 64 * s2 > 256) --s2;
     if (s2 >= 2 && stages > s2) stages = s2;
   }
+  if (use_ts)
+    while (stages > 2 && tmem_a_col + 64 * stages > 512) --stages;
+  int tmem_cols = 32;
+  while (tmem_cols < (use_ts ? tmem_a_col + 64 * stages : bn)) tmem_cols <<= 1;
   const size_t smem = stages * stage_bytes + (3 * stages + 2) * sizeof(uint64_t) + 1024;
 
   CUtensorMap ma, mbh, mbl, ma2;
@@ -462,15 +535,18 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
   else ma2 = ma;
   static bool configured = false;
   if (!configured) {
-    HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   GemmParams P;
   P.M = M; P.N = N; P.K = Ktot; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
   P.bias = bias; P.C = C; P.ldc = ldc; P.accumulate = accumulate; P.k_per_split = 0; P.split_stride = 0;
+  P.tmem_a_col = tmem_a_col;
   P.kb_first = K2 > 0 ? kb_first : 0x7fffffff;
   dim3 grid((M + kGmBM - 1) / kGmBM, ntiles);
-  gemm_tf32x3_kernel<0><<<grid, kGmThreads, smem, as_stream(stream)>>>(ma, mbh, mbl, ma2, P);
+  if (use_ts) gemm_tf32x3_kernel<0, 1><<<grid, kGmThreads, smem, as_stream(stream)>>>(ma, mbh, mbl, ma2, P);
+  else gemm_tf32x3_kernel<0, 0><<<grid, kGmThreads, smem, as_stream(stream)>>>(ma, mbh, mbl, ma2, P);
   HL_LAUNCH_CHECK("gemm_tf32x3_kernel");
   return HL_OK;
 }
@@ -573,7 +649,7 @@ extern "C" int hl_wgrad_tf32x3(const float* g, int64_t ld_g, const float* x, int
   GemmParams P;
   P.M = fo; P.N = fi; P.K = nrows; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
   P.bias = nullptr; P.C = reinterpret_cast<float*>(workspace); P.ldc = fi; P.accumulate = 0;
-  P.k_per_split = k_per_split; P.split_stride = (int64_t)fo * fi;
+  P.k_per_split = k_per_split; P.split_stride = (int64_t)fo * fi; P.tmem_a_col = 0;
   dim3 grid(mtiles, ntiles, splits);
   P.kb_first = 0;
   gemm_tf32x3_kernel<1><<<grid, kGmThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
