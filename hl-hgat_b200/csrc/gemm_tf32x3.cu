@@ -201,7 +201,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           // stack of {32 cols, 32 rows} boxes: 4 for the 128 output rows (G columns), bn/32 for the output columns
           gm_mbar_arrive_expect_tx(&full_bar[s], a_bytes + b_bytes);
           const int row = k_begin + kb * kGmBK;
-          for (int j = 0; j < kGmBM / 32; ++j) gm_tma_load_2d(st + j * 4096, &map_a, &full_bar[s], m0 + 32 * j, row);
+          if (TS) gm_tma_load_2d(st, &map_a, &full_bar[s], m0, row);       // plain [32 k-rows][128 m] tile for the converters
+          else
+            for (int j = 0; j < kGmBM / 32; ++j) gm_tma_load_2d(st + j * 4096, &map_a, &full_bar[s], m0 + 32 * j, row);
           for (int j = 0; j < bn / 32; ++j)
             gm_tma_load_2d(st + b_off + j * 4096, &map_bhi, &full_bar[s], n0 + 32 * j, row);
         }
@@ -212,7 +214,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (lane == 0) {
       // instruction descriptor: D=F32, A=B=TF32, K-major both, N = bn, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kGmBM >> 4) << 24) |
-                             (MODE == 1 ? ((1u << 15) | (1u << 16)) : 0u);
+                             (MODE == 1 ? ((TS ? 0u : (1u << 15)) | (1u << 16)) : 0u);   // A from TMEM is always K-major
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % stages;
         const uint32_t round = (uint32_t)(kb / stages);
@@ -224,8 +226,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           const uint32_t ta_hi = tmem_base + (uint32_t)P.tmem_a_col + (uint32_t)s * 64u, ta_lo = ta_hi + 32u;
 #pragma unroll
           for (int k = 0; k < kGmBK / 8; ++k) {
-            const uint32_t off = (uint32_t)k * 32u;
-            const uint64_t dbh = gm_desc_kmajor_sw128(b_hi + off), dbl = gm_desc_kmajor_sw128(b_lo + off);
+            const uint64_t dbh = MODE == 0 ? gm_desc_kmajor_sw128(b_hi + (uint32_t)k * 32u) : gm_desc_mnmajor_sw128(b_hi + (uint32_t)k * 1024u, 4096);
+            const uint64_t dbl = MODE == 0 ? gm_desc_kmajor_sw128(b_lo + (uint32_t)k * 32u) : gm_desc_mnmajor_sw128(b_lo + (uint32_t)k * 1024u, 4096);
             gm_mma_tf32_ts(tmem_base, ta_lo + 8u * k, dbh, idesc, (kb | k) ? 1u : 0u);   // small terms first
             gm_mma_tf32_ts(tmem_base, ta_hi + 8u * k, dbl, idesc, 1u);
             gm_mma_tf32_ts(tmem_base, ta_hi + 8u * k, dbh, idesc, 1u);
@@ -265,18 +267,44 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // split, and store hi | lo as 2 x 32 columns of the stage's TMEM slot
         const int quad = warp & 3;
         const int r = quad * 32 + lane;
-        const unsigned char* arow = base + (size_t)s * stage_bytes + (size_t)r * 128;
         uint32_t hi[32], lo[32];
+        if (MODE == 0) {
+          const unsigned char* arow = base + (size_t)s * stage_bytes + (size_t)r * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 x = *reinterpret_cast<const float4*>(arow + ((c ^ (r & 7)) << 4));
-          const float xs[4] = {x.x, x.y, x.z, x.w};
+          for (int c = 0; c < 8; ++c) {
+            const float4 x = *reinterpret_cast<const float4*>(arow + ((c ^ (r & 7)) << 4));
+            const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const uint32_t h = __float_as_uint(xs[t]) & 0xffffe000u;
-            hi[4 * c + t] = h;
-            lo[4 * c + t] = __float_as_uint(xs[t] - __uint_as_float(h));
+            for (int t = 0; t < 4; ++t) {
+              const uint32_t h = __float_as_uint(xs[t]) & 0xffffe000u;
+              hi[4 * c + t] = h;
+              lo[4 * c + t] = __float_as_uint(xs[t] - __uint_as_float(h));
+            }
           }
+        } else {
+          // weight gradient: A = G^T.  The G tile sits as [32 k-rows][128 m] (unswizzled); this thread's output row m = r
+          // is a column of it (consecutive lanes -> consecutive words: conflict-free)
+          const float* acol = reinterpret_cast<const float*>(base + (size_t)s * stage_bytes) + r;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float x = acol[k * kGmBM];
+            const uint32_t h = __float_as_uint(x) & 0xffffe000u;
+            hi[k] = h;
+            lo[k] = __float_as_uint(x - __uint_as_float(h));
+          }
+          float4* b = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + b_off);
+          float4* blo = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + b_off + b_bytes);
+          for (int idx = ct; idx < (int)(b_bytes / 16); idx += kGmConvThreads) {
+            const float4 x = b[idx];
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+            h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+            h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+            h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+            l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+            blo[idx] = l;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // B_lo (generic-proxy writes) -> visible to the MMA
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)P.tmem_a_col + (uint32_t)s * 64u;
         gm_tmem_st_x32(taddr, hi);
@@ -420,7 +448,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 
 // 2-D fp32 tensor [rows, cols] with row pitch ld (elements); box = {32 cols, box_rows}; 128-byte swizzle
 static bool make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows,
-                     int box_cols = kGmBK, bool mn_major = false) {
+                     int box_cols = kGmBK, bool mn_major = false, bool no_swizzle = false) {
   auto fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -428,7 +456,8 @@ static bool make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t c
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE,
+            no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : (mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -601,16 +630,41 @@ gm_split_reduce_kernel(const float* __restrict__ partial, int32_t splits, int64_
   }
 }
 
+// row splits of the weight gradient: tiles x splits CTAs fill `waves` rounds of the 148 SMs without spilling into
+// another one (one CTA per SM: the ring takes most of the shared memory).  One round measured best
+// (tools/wgrad_shapes_probe.py, sum over the ZINC stack: 0.70 ms vs 0.80 ms for two rounds, 0.89 ms for three): half
+// as many partial tiles to write and to reduce, and a k-loop twice as long per prologue / epilogue.
 static int wgrad_tc_splits(int32_t nrows, int tiles) {
-  int s = (2 * 148 + tiles - 1) / tiles;
+  static int waves = 0;
+  if (waves == 0) { const char* e = getenv("HL_WGRAD_WAVES"); waves = e ? atoi(e) : 1; if (waves < 1 || waves > 4) waves = 1; }
+  int s = (waves * 148) / tiles;
   const int max_s = (nrows + 255) / 256;
   if (s > max_s) s = max_s;
   return s < 1 ? 1 : s;
 }
 
+static int wgrad_max_bn() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("HL_WGRAD_MAX_BN");
+    v = e ? atoi(e) : 256;
+    if (v < 32 || v > 256 || v % 32 != 0) v = 256;
+  }
+  return v;
+}
+
+// column tiles of the weight gradient: 128 columns (64 KB / 48 KB ring stages, 3-4 in flight) from 256 input features
+// on, one tile of up to 256 columns below (measured, tools/wgrad_shapes_probe.py: 86.5 -> 75.5 us at 256 x 704,
+// 48 -> 37.6 us at 256 x 256, but 24.9 -> 30.2 us at 128 x 192 when split in two 96-column tiles)
+static int wgrad_ntiles(int32_t fi) {
+  const char* e = getenv("HL_WGRAD_MAX_BN");
+  const int max_bn = e ? wgrad_max_bn() : (fi >= 256 ? 128 : 256);
+  return (fi + max_bn - 1) / max_bn;
+}
+
 extern "C" size_t hl_wgrad_tf32x3_workspace(int32_t nrows, int32_t fo, int32_t fi) {
   if (nrows < 0 || fo < 1 || fi < 1) return 0;
-  const int ntiles = (fi + 255) / 256;
+  const int ntiles = wgrad_ntiles(fi);
   const int tiles = ((fo + hl::kGmBM - 1) / hl::kGmBM) * ntiles;
   return (size_t)wgrad_tc_splits(nrows, tiles) * (size_t)fo * (size_t)fi * sizeof(float) + 256;
 }
@@ -626,33 +680,42 @@ extern "C" int hl_wgrad_tf32x3(const float* g, int64_t ld_g, const float* x, int
   if (ld_g % 4 != 0 || ld_x % 4 != 0 || !aligned_to(g, 16) || !aligned_to(x, 16)) return 1;
   if (fo % 4 != 0 || fi % 32 != 0 || nrows < 512) return 1;
   if (!workspace || workspace_bytes < hl_wgrad_tf32x3_workspace(nrows, fo, fi)) return HL_ERR_WORKSPACE;
-  const int ntiles = (fi + 255) / 256;
+  const int ntiles = wgrad_ntiles(fi);
   const int bn = ((fi + ntiles - 1) / ntiles + 31) / 32 * 32;     // multiple of 32: whole {32 x 32} boxes
-  int tmem_cols = 32;
-  while (tmem_cols < bn) tmem_cols <<= 1;
-  const size_t stage_bytes = 2 * (size_t)kGmBM * kGmBK * 4 + 2 * (size_t)bn * kGmBK * 4;
+  static int use_ts = -1;
+  if (use_ts < 0) { const char* e = getenv("HL_WGRAD_TS"); use_ts = e ? atoi(e) : 1; }
+  const size_t stage_bytes = (use_ts ? 1 : 2) * (size_t)kGmBM * kGmBK * 4 + 2 * (size_t)bn * kGmBK * 4;
   int stages = (int)((200 * 1024) / stage_bytes);
   if (stages > 4) stages = 4;
   if (stages < 2) return 1;
+  const int tmem_a_col = (bn + 31) / 32 * 32;
+  if (use_ts)
+    while (stages > 2 && tmem_a_col + 64 * stages > 512) --stages;
+  int tmem_cols = 32;
+  while (tmem_cols < (use_ts ? tmem_a_col + 64 * stages : bn)) tmem_cols <<= 1;
   const size_t smem = stages * stage_bytes + (3 * stages + 2) * sizeof(uint64_t) + 1024;
   const int mtiles = (fo + kGmBM - 1) / kGmBM;
   const int splits = wgrad_tc_splits(nrows, mtiles * ntiles);
   const int k_per_split = ((nrows + splits - 1) / splits + 31) / 32 * 32;
 
   CUtensorMap mg, mx;
-  if (!make_map(&mg, g, nrows, fo, ld_g, 32, 32, true) || !make_map(&mx, x, nrows, fi, ld_x, 32, 32, true)) return 1;
+  if (use_ts ? !make_map(&mg, g, nrows, fo, ld_g, 32, kGmBM, false, true) : !make_map(&mg, g, nrows, fo, ld_g, 32, 32, true)) return 1;
+  if (!make_map(&mx, x, nrows, fi, ld_x, 32, 32, true)) return 1;
   static bool configured = false;
   if (!configured) {
-    HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   GemmParams P;
   P.M = fo; P.N = fi; P.K = nrows; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
   P.bias = nullptr; P.C = reinterpret_cast<float*>(workspace); P.ldc = fi; P.accumulate = 0;
-  P.k_per_split = k_per_split; P.split_stride = (int64_t)fo * fi; P.tmem_a_col = 0;
+  P.k_per_split = k_per_split; P.split_stride = (int64_t)fo * fi; P.tmem_a_col = tmem_a_col;
   dim3 grid(mtiles, ntiles, splits);
   P.kb_first = 0;
-  gemm_tf32x3_kernel<1><<<grid, kGmThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
+  if (use_ts) gemm_tf32x3_kernel<1, 1><<<grid, kGmThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
+  else
+  gemm_tf32x3_kernel<1, 0><<<grid, kGmThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
   HL_LAUNCH_CHECK("gemm_tf32x3_kernel<wgrad>");
   const int64_t n = (int64_t)fo * fi;
   gm_split_reduce_kernel<<<(int)((n * 2 + 255) / 256), 256, 0, as_stream(stream)>>>(P.C, splits, P.split_stride, fo, fi, dw, ld_dw,
