@@ -128,6 +128,7 @@ struct GemmParams {
   int32_t k_per_split;      // wgrad mode: rows of the contraction handled by one blockIdx.z (multiple of 32)
   int64_t split_stride;     // wgrad mode: elements between partial outputs of consecutive splits
   int32_t tmem_a_col;       // TS variant: first TMEM column of the A_hi | A_lo slots (64 columns per ring stage)
+  float* colsum_ws;         // wgrad TS: per-split column sums of G, [splits][M] (the bias gradient falls out of the A pass)
 };
 
 // MODE 0: C = A[M,K] B[N,K]^T, both K-major, B pre-split (map_b = hi, map_b2 = lo).
@@ -258,6 +259,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   } else {
     // ------------------------------------ converters, then epilogue ------------------------------------
     const int ct = threadIdx.x - 64;                                // 0..127
+    float csum = 0.f;                                               // wgrad TS: running sum of this thread's G column
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % stages;
       const uint32_t round = (uint32_t)(kb / stages);
@@ -288,6 +290,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             const float x = acol[k * kGmBM];
+            csum += x;
             const uint32_t h = __float_as_uint(x) & 0xffffe000u;
             hi[k] = h;
             lo[k] = __float_as_uint(x - __uint_as_float(h));
@@ -344,6 +347,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
       gm_mbar_arrive(&conv_bar[s]);
+    }
+    if (MODE == 1 && TS && P.colsum_ws && blockIdx.y == 0) {
+      const int m = m0 + (warp & 3) * 32 + lane;
+      if (m < P.M) P.colsum_ws[(int64_t)blockIdx.z * P.M + m] = csum;
     }
     // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (= output rows)
     gm_mbar_wait(acc_bar, 0);
@@ -571,7 +578,7 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
   GemmParams P;
   P.M = M; P.N = N; P.K = Ktot; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
   P.bias = bias; P.C = C; P.ldc = ldc; P.accumulate = accumulate; P.k_per_split = 0; P.split_stride = 0;
-  P.tmem_a_col = tmem_a_col;
+  P.tmem_a_col = tmem_a_col; P.colsum_ws = nullptr;
   P.kb_first = K2 > 0 ? kb_first : 0x7fffffff;
   dim3 grid((M + kGmBM - 1) / kGmBM, ntiles);
   if (use_ts) gemm_tf32x3_kernel<0, 1><<<grid, kGmThreads, smem, as_stream(stream)>>>(ma, mbh, mbl, ma2, P);
@@ -584,16 +591,20 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
 // plane and lane: k = lane, lane + 8, ...; whole 32-byte sectors of every plane), fixed shuffle tree -> deterministic
 __global__ void __launch_bounds__(256)
 gm_split_reduce_kernel(const float* __restrict__ partial, int32_t splits, int64_t split_stride, int32_t fo,
-                       int32_t fi, float* __restrict__ dw, int64_t ld_dw, int accumulate) {
+                       int32_t fi, float* __restrict__ dw, int64_t ld_dw, int accumulate,
+                       const float* __restrict__ cs_partial, float* __restrict__ dbias, int accumulate_bias) {
   const int64_t n4 = ((int64_t)fo * fi) >> 2;                      // fi % 32 == 0: rows never straddle a float4
+  const int64_t c4 = dbias ? (fo >> 2) : 0;                         // + the [splits][fo] column sums of G (bias gradient)
+  const int64_t tot4 = n4 + c4;
   const int sub = threadIdx.x & 7;
   const bool vec_out = (ld_dw % 4 == 0) && ((reinterpret_cast<uintptr_t>(dw) & 15) == 0);
-  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < ((n4 + 3) & ~(int64_t)3);
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < ((tot4 + 3) & ~(int64_t)3);
        i += ((int64_t)gridDim.x * blockDim.x) >> 3) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < n4) {
-      const float4* p = reinterpret_cast<const float4*>(partial) + i;
-      const int64_t stride4 = split_stride >> 2;
+    if (i < tot4) {
+      const bool is_cs = i >= n4;
+      const float4* p = is_cs ? reinterpret_cast<const float4*>(cs_partial) + (i - n4) : reinterpret_cast<const float4*>(partial) + i;
+      const int64_t stride4 = is_cs ? (int64_t)(fo >> 2) : (split_stride >> 2);
       int k = sub;
       for (; k + 24 < splits; k += 32) {
         float4 v[4];
@@ -613,6 +624,11 @@ gm_split_reduce_kernel(const float* __restrict__ partial, int32_t splits, int64_
       s.y += __shfl_xor_sync(0xffffffffu, s.y, m);
       s.z += __shfl_xor_sync(0xffffffffu, s.z, m);
       s.w += __shfl_xor_sync(0xffffffffu, s.w, m);
+    }
+    if (sub == 0 && i >= n4 && i < tot4) {
+      float* q = dbias + ((i - n4) << 2);
+      q[0] = accumulate_bias ? q[0] + s.x : s.x; q[1] = accumulate_bias ? q[1] + s.y : s.y;
+      q[2] = accumulate_bias ? q[2] + s.z : s.z; q[3] = accumulate_bias ? q[3] + s.w : s.w;
     }
     if (sub == 0 && i < n4) {
       const int64_t e = i << 2;
@@ -666,14 +682,29 @@ extern "C" size_t hl_wgrad_tf32x3_workspace(int32_t nrows, int32_t fo, int32_t f
   if (nrows < 0 || fo < 1 || fi < 1) return 0;
   const int ntiles = wgrad_ntiles(fi);
   const int tiles = ((fo + hl::kGmBM - 1) / hl::kGmBM) * ntiles;
-  return (size_t)wgrad_tc_splits(nrows, tiles) * (size_t)fo * (size_t)fi * sizeof(float) + 256;
+  const size_t splits = (size_t)wgrad_tc_splits(nrows, tiles);
+  return hl::align_up(splits * (size_t)fo * (size_t)fi * sizeof(float), 256) + splits * (size_t)fo * sizeof(float) + 256;
 }
+
+extern "C" int hl_wgrad_bias_tf32x3(const float* g, int64_t ld_g, const float* x, int64_t ld_x, int32_t nrows, int32_t fo,
+                                    int32_t fi, float* dw, int64_t ld_dw, int accumulate, float* dbias, int accumulate_bias,
+                                    void* workspace, size_t workspace_bytes, hl_stream_t stream);
 
 // dW[fo,fi] (=|+=) g[R,fo]^T x[R,fi] on the tensor cores (3xTF32), split over row ranges, partial tiles summed
 // in a fixed order.  Returns 1 when the shape is unsupported (caller falls back to hl_wgrad).
 extern "C" int hl_wgrad_tf32x3(const float* g, int64_t ld_g, const float* x, int64_t ld_x, int32_t nrows, int32_t fo,
                                int32_t fi, float* dw, int64_t ld_dw, int accumulate, void* workspace,
                                size_t workspace_bytes, hl_stream_t stream) {
+  return hl_wgrad_bias_tf32x3(g, ld_g, x, ld_x, nrows, fo, fi, dw, ld_dw, accumulate, nullptr, 0, workspace, workspace_bytes,
+                              stream);
+}
+
+// ... and, when dbias != NULL, dbias[fo] (=|+=) column sums of g in the same two launches: the converter warps that move
+// G^T into tensor memory add up their column as they go.  Returns 2 (dW done, dbias NOT done: use hl_colsum) when the
+// variant in use cannot fold the bias in.
+extern "C" int hl_wgrad_bias_tf32x3(const float* g, int64_t ld_g, const float* x, int64_t ld_x, int32_t nrows, int32_t fo,
+                                    int32_t fi, float* dw, int64_t ld_dw, int accumulate, float* dbias, int accumulate_bias,
+                                    void* workspace, size_t workspace_bytes, hl_stream_t stream) {
   using namespace hl;
   if (nrows < 0 || fo < 1 || fi < 1 || !dw) return HL_ERR_INVALID;
   if (nrows > 0 && (!g || !x)) return HL_ERR_INVALID;
@@ -711,6 +742,10 @@ extern "C" int hl_wgrad_tf32x3(const float* g, int64_t ld_g, const float* x, int
   P.M = fo; P.N = fi; P.K = nrows; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
   P.bias = nullptr; P.C = reinterpret_cast<float*>(workspace); P.ldc = fi; P.accumulate = 0;
   P.k_per_split = k_per_split; P.split_stride = (int64_t)fo * fi; P.tmem_a_col = tmem_a_col;
+  const bool fold_bias = dbias && use_ts;
+  float* cs_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) +
+                                          align_up((size_t)splits * (size_t)fo * (size_t)fi * sizeof(float), 256));
+  P.colsum_ws = fold_bias ? cs_ws : nullptr;
   dim3 grid(mtiles, ntiles, splits);
   P.kb_first = 0;
   if (use_ts) gemm_tf32x3_kernel<1, 1><<<grid, kGmThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
@@ -718,8 +753,8 @@ extern "C" int hl_wgrad_tf32x3(const float* g, int64_t ld_g, const float* x, int
   gemm_tf32x3_kernel<1, 0><<<grid, kGmThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
   HL_LAUNCH_CHECK("gemm_tf32x3_kernel<wgrad>");
   const int64_t n = (int64_t)fo * fi;
-  gm_split_reduce_kernel<<<(int)((n * 2 + 255) / 256), 256, 0, as_stream(stream)>>>(P.C, splits, P.split_stride, fo, fi, dw, ld_dw,
-                                                                               accumulate);
+  gm_split_reduce_kernel<<<(int)(((n + (fold_bias ? fo : 0)) * 2 + 255) / 256), 256, 0, as_stream(stream)>>>(
+      P.C, splits, P.split_stride, fo, fi, dw, ld_dw, accumulate, cs_ws, fold_bias ? dbias : nullptr, accumulate_bias);
   HL_LAUNCH_CHECK("gm_split_reduce_kernel");
-  return HL_OK;
+  return (dbias && !fold_bias) ? 2 : HL_OK;
 }

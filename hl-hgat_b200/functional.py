@@ -296,8 +296,10 @@ def dense2(a1, w1, a2, w2, bias=None, out=None, accumulate=False):
     return dense(a2, w2, None, out=out, accumulate=True)
 
 
-def wgrad(g, x, out=None, accumulate=False):
-    """dW[Fo,Fi] (=|+=) g[R,Fo]^T x[R,Fi] (deterministic split-row reduction); `out` may be a column slice."""
+def wgrad(g, x, out=None, accumulate=False, bias_out=None, bias_accumulate=False):
+    """dW[Fo,Fi] (=|+=) g[R,Fo]^T x[R,Fi] (deterministic split-row reduction); `out` may be a column slice.
+    `bias_out` [Fo] (optional): also (=|+=) the column sums of g -- folded into the tensor-core launch when it can
+    be (the converter warps that move g^T into tensor memory add up their column), else through hl_colsum."""
     L = N.lib()
     g, ldg = N.row_major(g)
     x, ldx = N.row_major(x)
@@ -307,20 +309,34 @@ def wgrad(g, x, out=None, accumulate=False):
         out = torch.empty((fo, fi), dtype=torch.float32, device=g.device)
         accumulate = False
     acc = 1 if accumulate else 0
+    done = False
     if _GEMM_MODE["tensor"]:
         nb = L.hl_wgrad_tf32x3_workspace(R, fo, fi)
         ws = torch.empty(nb, dtype=torch.uint8, device=g.device)
-        rc = L.hl_wgrad_tf32x3(g.data_ptr(), ldg, x.data_ptr(), ldx, R, fo, fi, out.data_ptr(), out.stride(0), acc,
-                               ws.data_ptr(), nb, N.stream_ptr())
-        if rc == 0:
-            return out
-        if rc != 1:
-            N.check(rc, "hl_wgrad_tf32x3")
-    nb = L.hl_wgrad_workspace(R, fo, fi)
-    ws = torch.empty(nb, dtype=torch.uint8, device=g.device)
-    N.check(L.hl_wgrad(g.data_ptr(), ldg, x.data_ptr(), ldx, R, fo, fi, out.data_ptr(), out.stride(0), acc,
-                       ws.data_ptr(), nb, N.stream_ptr()), "hl_wgrad")
+        rc = L.hl_wgrad_bias_tf32x3(g.data_ptr(), ldg, x.data_ptr(), ldx, R, fo, fi, out.data_ptr(), out.stride(0), acc,
+                                    N.ptr(bias_out), 1 if bias_accumulate else 0, ws.data_ptr(), nb, N.stream_ptr())
+        if rc == 0 or rc == 2:
+            done = True
+            if rc == 0:
+                bias_out = None                      # folded in
+        elif rc != 1:
+            N.check(rc, "hl_wgrad_bias_tf32x3")
+    if not done:
+        nb = L.hl_wgrad_workspace(R, fo, fi)
+        ws = torch.empty(nb, dtype=torch.uint8, device=g.device)
+        N.check(L.hl_wgrad(g.data_ptr(), ldg, x.data_ptr(), ldx, R, fo, fi, out.data_ptr(), out.stride(0), acc,
+                           ws.data_ptr(), nb, N.stream_ptr()), "hl_wgrad")
+    if bias_out is not None:
+        _colsum_into(g, ldg, bias_out, bias_accumulate)
     return out
+
+
+def _colsum_into(g, ldg, out, accumulate):
+    L = N.lib()
+    R, f = g.shape
+    nb = L.hl_colsum_workspace(R, f)
+    ws = torch.empty(nb, dtype=torch.uint8, device=g.device)
+    N.check(L.hl_colsum(g.data_ptr(), ldg, R, f, out.data_ptr(), 1 if accumulate else 0, ws.data_ptr(), nb, N.stream_ptr()), "hl_colsum")
 
 
 def colsum(g, out=None):
@@ -362,20 +378,29 @@ class _Linear(torch.autograd.Function):
         g = g.contiguous()
         d = xa.shape[1]
         ga = gb = gw = gbias = None
+        want_bias = ctx.has_bias and ctx.needs_input_grad[3]
+        tgt_b = _grad_target(ctx.params[1]) if want_bias else None
         if ctx.needs_input_grad[2]:
             tgt = _grad_target(ctx.params[0])
+            fold = want_bias and (tgt is None) == (tgt_b is None)      # bias gradient rides on the first weight-gradient launch
+            if fold:
+                gbias = tgt_b if tgt_b is not None else torch.empty(weight.shape[0], dtype=torch.float32, device=g.device)
             with _wgrad_lane(tgt is not None, g, xa, xb):
                 gw = torch.empty_like(weight) if tgt is None else tgt
-                wgrad(g, xa, gw[:, :d], accumulate=tgt is not None)
+                wgrad(g, xa, gw[:, :d], accumulate=tgt is not None, bias_out=gbias if fold else None,
+                      bias_accumulate=tgt_b is not None)
                 if xb is not None:
                     wgrad(g, xb, gw[:, d:], accumulate=tgt is not None)
             if tgt is not None:
                 gw = None
-        if ctx.has_bias and ctx.needs_input_grad[3]:
-            tgt = _grad_target(ctx.params[1])
-            with _wgrad_lane(tgt is not None, g):
-                gbias = colsum(g, out=tgt)
-            if tgt is not None:
+            if fold:
+                want_bias = False
+                if tgt_b is not None:
+                    gbias = None
+        if want_bias:
+            with _wgrad_lane(tgt_b is not None, g):
+                gbias = colsum(g, out=tgt_b)
+            if tgt_b is not None:
                 gbias = None
         if ctx.needs_input_grad[0]:
             ga = dense(g, weight[:, :d], transpose_w=True)
@@ -421,22 +446,31 @@ class _PolyConv(torch.autograd.Function):
         R, width = x.shape
         g = g.contiguous()
         need_x = ctx.needs_input_grad[0]
+        want_bias = ctx.has_bias and ctx.needs_input_grad[1]
+        tgt_b = _grad_target(ctx.params[0]) if want_bias else None
+        gb = None
         gws = []
         for k in range(K):
             if ctx.needs_input_grad[5 + k]:
                 src = x if k == 0 else t[k - 1]
                 tgt = _grad_target(ctx.params[1][k])
+                fold = want_bias and (tgt is None) == (tgt_b is None) and g.shape[0] == src.numel() // inner
+                if fold:                                   # bias gradient rides on this weight-gradient launch
+                    gb = tgt_b if tgt_b is not None else torch.empty(g.shape[1], dtype=torch.float32, device=g.device)
                 with _wgrad_lane(tgt is not None, g, src):
-                    gw = wgrad(g, src.view(-1, inner), out=tgt, accumulate=tgt is not None)
+                    gw = wgrad(g, src.view(-1, inner), out=tgt, accumulate=tgt is not None, bias_out=gb if fold else None,
+                               bias_accumulate=tgt_b is not None)
+                if fold:
+                    want_bias = False
+                    if tgt_b is not None:
+                        gb = None
                 gws.append(None if tgt is not None else gw)
             else:
                 gws.append(None)
-        gb = None
-        if ctx.has_bias and ctx.needs_input_grad[1]:
-            tgt = _grad_target(ctx.params[0])
-            with _wgrad_lane(tgt is not None, g):
-                gb = colsum(g, out=tgt)
-            if tgt is not None:
+        if want_bias:
+            with _wgrad_lane(tgt_b is not None, g):
+                gb = colsum(g, out=tgt_b)
+            if tgt_b is not None:
                 gb = None
         gx = None
         if need_x:

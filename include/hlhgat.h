@@ -334,6 +334,11 @@ size_t hl_wgrad_tf32x3_workspace(int32_t nrows, int32_t fo, int32_t fi);
 int hl_wgrad_tf32x3(const float* g, int64_t ld_g, const float* x, int64_t ld_x, int32_t nrows, int32_t fo, int32_t fi,
                     float* dw, int64_t ld_dw, int accumulate, void* workspace, size_t workspace_bytes,
                     hl_stream_t stream);
+/* The same, plus dbias[fo] (=|+=) the column sums of g (the bias gradient of the Linear / conv whose weight gradient
+ * this is) folded into the same two launches.  Returns 2 when dW was computed but dbias was not (use hl_colsum). */
+int hl_wgrad_bias_tf32x3(const float* g, int64_t ld_g, const float* x, int64_t ld_x, int32_t nrows, int32_t fo, int32_t fi,
+                         float* dw, int64_t ld_dw, int accumulate, float* dbias /* nullable */, int accumulate_bias,
+                         void* workspace, size_t workspace_bytes, hl_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
  * Weight and bias gradients of the dense layers as deterministic split-row reductions.

@@ -419,6 +419,31 @@ def test_tcgen05_wgrad_vs_fp64(R, fo, fi):
     assert torch.equal(F_hl.wgrad(g, x), got)
 
 
+@pytest.mark.parametrize("R,fo,fi", [(1472, 256, 448), (24001, 64, 64), (3000, 128, 192), (5000, 12, 96), (300, 64, 64)])
+def test_wgrad_with_folded_bias_gradient(R, fo, fi):
+    """dbias = column sums of g from the same launches as dW (the converter warps that move g^T into tensor memory add
+    up their column); shapes the tensor-core kernel does not take fall back to hl_wgrad + hl_colsum."""
+    torch.manual_seed(R + fo)
+    g, x = torch.randn(R, fo, device=DEV) + 0.3, torch.randn(R, fi, device=DEV)
+    ref_w, ref_b = g.double().t() @ x.double(), g.double().sum(0)
+    db = torch.full((fo,), float("nan"), device=DEV)
+    dw = F_hl.wgrad(g, x, bias_out=db)
+    assert float((dw.double() - ref_w).abs().max()) < 1e-4 * float(ref_w.abs().max())
+    assert float((db.double() - ref_b).abs().max()) < 1e-5 * float(ref_b.abs().max())
+    assert torch.equal(dw, F_hl.wgrad(g, x))                     # the fold does not change dW
+    # accumulation into existing gradients (fused mode), weight as a column slice of a wider matrix
+    wide = torch.randn(fo, fi + 32, device=DEV)
+    acc_b = torch.randn(fo, device=DEV)
+    want_w, want_b = wide[:, :fi].double() + ref_w, acc_b.double() + ref_b
+    F_hl.wgrad(g, x, out=wide[:, :fi], accumulate=True, bias_out=acc_b, bias_accumulate=True)
+    assert float((wide[:, :fi].double() - want_w).abs().max()) < 1e-4 * float(ref_w.abs().max())
+    assert float((acc_b.double() - want_b).abs().max()) < 1e-5 * float(ref_b.abs().max())
+    # deterministic
+    db2 = torch.empty(fo, device=DEV)
+    F_hl.wgrad(g, x, bias_out=db2)
+    assert torch.equal(db, db2)
+
+
 def test_bn_running_stats_match_torch():
     torch.manual_seed(3)
     x = torch.randn(777, 48) * 2 + 1
