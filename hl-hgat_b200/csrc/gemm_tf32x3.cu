@@ -29,8 +29,8 @@ namespace hl {
 
 constexpr int kGmBM = 128;
 constexpr int kGmBK = 32;                 // floats per k-block = one 128-byte swizzle span
-constexpr int kGmThreads = 192;
-constexpr int kGmConvThreads = 128;
+constexpr int kGmThreads = 320;           // warp 0 TMA, warp 1 MMA issue, warps 2-5 and 6-9: two converter groups
+constexpr int kGmConvThreads = 128;       // threads per converter group (one thread per tile row / TMEM lane)
 
 __device__ __forceinline__ uint32_t gm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -128,6 +128,7 @@ struct GemmParams {
   int32_t k_per_split;      // wgrad mode: rows of the contraction handled by one blockIdx.z (multiple of 32)
   int64_t split_stride;     // wgrad mode: elements between partial outputs of consecutive splits
   int32_t tmem_a_col;       // TS variant: first TMEM column of the A_hi | A_lo slots (64 columns per ring stage)
+  int32_t conv_groups;      // converter groups taking alternate ring stages: 1 (192 threads) or 2 (320 threads)
   float* colsum_ws;         // wgrad TS: per-split column sums of G, [splits][M] (the bias gradient falls out of the A pass)
 };
 
@@ -258,9 +259,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
   } else {
     // ------------------------------------ converters, then epilogue ------------------------------------
-    const int ct = threadIdx.x - 64;                                // 0..127
+    // Weight gradient (TS): two converter groups take alternate ring stages -- one stage's chain (transposed LDS of G,
+    // split of X in shared memory, tcgen05.st, wait::st) is longer than its MMAs, so a single group was the serial
+    // bottleneck of the ring (256 x 704: 61.8 -> 51.7 us).  The forward kernel gains nothing from a second group
+    // (92.1 vs 93.4 us, small shapes slightly slower) and runs with one; the groups share the epilogue.
+    const int groups = P.conv_groups;
+    const int cg = (warp - 2) >> 2;                                  // converter group 0 / 1
+    const int ct = (threadIdx.x - 64) & (kGmConvThreads - 1);       // 0..127 inside the group
     float csum = 0.f;                                               // wgrad TS: running sum of this thread's G column
-    for (int kb = 0; kb < num_kb; ++kb) {
+    for (int kb = cg; kb < num_kb; kb += groups) {
       const int s = kb % stages;
       const uint32_t round = (uint32_t)(kb / stages);
       gm_mbar_wait(&full_bar[s], round & 1u);
@@ -350,7 +357,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
     if (MODE == 1 && TS && P.colsum_ws && blockIdx.y == 0) {
       const int m = m0 + (warp & 3) * 32 + lane;
-      if (m < P.M) P.colsum_ws[(int64_t)blockIdx.z * P.M + m] = csum;
+      if (m < P.M) P.colsum_ws[((int64_t)blockIdx.z * 2 + cg) * P.M + m] = csum;   // one plane per split and group
     }
     // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (= output rows)
     gm_mbar_wait(acc_bar, 0);
@@ -359,7 +366,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int quad = warp & 3;
     const int row = m0 + quad * 32 + lane;
     const bool vec_ok = (P.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
-    for (int c = 0; c < bn; c += 32) {
+    for (int c = 32 * cg; c < bn; c += 32 * groups) {                // the groups take alternate 32-column chunks
       uint32_t r[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c;
       asm volatile(
@@ -578,11 +585,11 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
   GemmParams P;
   P.M = M; P.N = N; P.K = Ktot; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
   P.bias = bias; P.C = C; P.ldc = ldc; P.accumulate = accumulate; P.k_per_split = 0; P.split_stride = 0;
-  P.tmem_a_col = tmem_a_col; P.colsum_ws = nullptr;
+  P.tmem_a_col = tmem_a_col; P.colsum_ws = nullptr; P.conv_groups = 1;
   P.kb_first = K2 > 0 ? kb_first : 0x7fffffff;
   dim3 grid((M + kGmBM - 1) / kGmBM, ntiles);
-  if (use_ts) gemm_tf32x3_kernel<0, 1><<<grid, kGmThreads, smem, as_stream(stream)>>>(ma, mbh, mbl, ma2, P);
-  else gemm_tf32x3_kernel<0, 0><<<grid, kGmThreads, smem, as_stream(stream)>>>(ma, mbh, mbl, ma2, P);
+  if (use_ts) gemm_tf32x3_kernel<0, 1><<<grid, 64 + kGmConvThreads, smem, as_stream(stream)>>>(ma, mbh, mbl, ma2, P);
+  else gemm_tf32x3_kernel<0, 0><<<grid, 64 + kGmConvThreads, smem, as_stream(stream)>>>(ma, mbh, mbl, ma2, P);
   HL_LAUNCH_CHECK("gemm_tf32x3_kernel");
   return HL_OK;
 }
@@ -606,14 +613,15 @@ gm_split_reduce_kernel(const float* __restrict__ partial, int32_t splits, int64_
       const float4* p = is_cs ? reinterpret_cast<const float4*>(cs_partial) + (i - n4) : reinterpret_cast<const float4*>(partial) + i;
       const int64_t stride4 = is_cs ? (int64_t)(fo >> 2) : (split_stride >> 2);
       int k = sub;
-      for (; k + 24 < splits; k += 32) {
+      const int planes = is_cs ? 2 * splits : splits;               // column sums: one plane per split and converter group
+      for (; k + 24 < planes; k += 32) {
         float4 v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) v[u] = __ldg(p + (int64_t)(k + 8 * u) * stride4);
 #pragma unroll
         for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
       }
-      for (; k < splits; k += 8) {
+      for (; k < planes; k += 8) {
         const float4 v = __ldg(p + (int64_t)k * stride4);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       }
@@ -683,7 +691,7 @@ extern "C" size_t hl_wgrad_tf32x3_workspace(int32_t nrows, int32_t fo, int32_t f
   const int ntiles = wgrad_ntiles(fi);
   const int tiles = ((fo + hl::kGmBM - 1) / hl::kGmBM) * ntiles;
   const size_t splits = (size_t)wgrad_tc_splits(nrows, tiles);
-  return hl::align_up(splits * (size_t)fo * (size_t)fi * sizeof(float), 256) + splits * (size_t)fo * sizeof(float) + 256;
+  return hl::align_up(splits * (size_t)fo * (size_t)fi * sizeof(float), 256) + 2 * splits * (size_t)fo * sizeof(float) + 256;
 }
 
 extern "C" int hl_wgrad_bias_tf32x3(const float* g, int64_t ld_g, const float* x, int64_t ld_x, int32_t nrows, int32_t fo,
@@ -745,12 +753,11 @@ extern "C" int hl_wgrad_bias_tf32x3(const float* g, int64_t ld_g, const float* x
   const bool fold_bias = dbias && use_ts;
   float* cs_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) +
                                           align_up((size_t)splits * (size_t)fo * (size_t)fi * sizeof(float), 256));
-  P.colsum_ws = fold_bias ? cs_ws : nullptr;
+  P.colsum_ws = fold_bias ? cs_ws : nullptr; P.conv_groups = use_ts ? 2 : 1;
   dim3 grid(mtiles, ntiles, splits);
   P.kb_first = 0;
   if (use_ts) gemm_tf32x3_kernel<1, 1><<<grid, kGmThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
-  else
-  gemm_tf32x3_kernel<1, 0><<<grid, kGmThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
+  else gemm_tf32x3_kernel<1, 0><<<grid, 64 + kGmConvThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
   HL_LAUNCH_CHECK("gemm_tf32x3_kernel<wgrad>");
   const int64_t n = (int64_t)fo * fi;
   gm_split_reduce_kernel<<<(int)(((n + (fold_bias ? fo : 0)) * 2 + 255) / 256), 256, 0, as_stream(stream)>>>(
