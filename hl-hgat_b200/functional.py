@@ -1,7 +1,8 @@
 """Differentiable host-side wrappers (torch.autograd.Function) over the C ABI.
 
-Forward and backward both run hand-written sm_100a kernels from libhlhgat.so; the only library
-calls are the dense Theta / MLP GEMMs (cuBLAS through torch.mm), as DESIGN.md states.
+Forward and backward both run hand-written sm_100a kernels from libhlhgat.so, including the dense Theta / MLP
+transforms and their data / weight / bias gradients (tcgen05 3xTF32); cuBLAS (through torch.mm) is only the
+fallback for dense shapes the tensor-core kernels do not take.
 """
 import contextlib
 import ctypes as C
