@@ -233,6 +233,7 @@ def run_ours(args, world, rank, local):
     from hlhgat_b200 import functional as F_hl
     F_hl.enable_factored_hodge1(factored)
     hlhgat_b200.enable_lanes(args.lanes == "on")
+    hlhgat_b200.enable_project_then_transfer(args.project_first == "on")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     torch.manual_seed(0)
@@ -320,6 +321,8 @@ def run_ours(args, world, rank, local):
                                     f"to a fixed capacity ({cap_txt}, ~2% ghost rows), then all-reduce + fused Adam graph"
                                     + ("; node chain and edge chain of every layer on two streams = two parallel branches of the graph"
                                        if args.lanes == "on" else ""),
+                       "transfer": ("project-then-transfer in NodeEdgeInt: (1/D)|B1| (x W_a^T) instead of ((1/D)|B1| x) W_a^T"
+                                    if args.project_first == "on" else "transfer-then-project (the reference's order)"),
                        "edge_operator": ("L1 applied in factored form diag(2/lambda) B1^T B1 (opt-in, fp32-rounding-equal to the CSR path)"
                                          if factored else "L1 applied from its CSR (bit-exact summation order of the reference)"),
                        "gemm": "dense Theta/MLP transforms + data/weight gradients: hand-written tcgen05 3xTF32 kernels (fp32-accurate); "
@@ -407,6 +410,9 @@ def main():
     ap.add_argument("--pool", type=int, default=POOL, help="distinct synthetic batches cycled through")
     ap.add_argument("--lanes", default="on", choices=["on", "off"],
                     help="issue the node chain and the edge chain of every layer on two CUDA streams (bit-identical results)")
+    ap.add_argument("--project-first", default="off", choices=["on", "off"],
+                    help="NodeEdgeInt applies W_a before the node<->edge transfer when the layer is narrower than the "
+                         "dense-connection buffer (transfers move f instead of d columns; fp32-rounding-equal)")
     ap.add_argument("--factored-l1", default="auto", choices=["auto", "on", "off"],
                     help="apply the edge Laplacian as diag(2/lambda) B1^T B1 instead of its CSR; auto = only for the long-row "
                          "workloads (cifar, tsp); the ZINC headline always uses the CSR SpMM")

@@ -414,6 +414,80 @@ def linear(x, weight, bias=None, x2=None):
     return _Linear.apply(x, x2, weight, bias)
 
 
+class _LinearPart(torch.autograd.Function):
+    """y = x W[:, c0:c1]^T (+ b) (+ addend): one column block of a Linear applied on its own, optionally
+    accumulated IN PLACE onto `addend` (a fresh tensor nobody else reads, e.g. a transfer result).  Lets the
+    NodeEdgeInt MLP project before it transfers: (1/D)|B1| (x_s Wa^T) + x_t Wb^T + b instead of
+    [(1/D)|B1| x_s | x_t] W^T + b (lib/Hodge_Cheb_Conv.py:294, :307-308) -- the transfer then moves the layer width f
+    instead of the dense-connection width d."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, addend, c0, c1):
+        N.require_cuda_f32(x, weight, bias, addend)
+        x = x.contiguous() if x.stride(1) != 1 else x
+        w = weight[:, c0:c1]
+        if addend is None:
+            y = dense(x, w, bias)
+        else:
+            y = dense(x, w, bias, out=addend, accumulate=True)
+            ctx.mark_dirty(addend)
+        ctx.save_for_backward(x, weight)
+        ctx.cols = (c0, c1)
+        ctx.params = (weight, bias)
+        ctx.has_bias, ctx.has_addend = bias is not None, addend is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        c0, c1 = ctx.cols
+        g = g.contiguous()
+        gx = gw = gbias = None
+        want_bias = ctx.has_bias and ctx.needs_input_grad[2]
+        tgt_b = _grad_target(ctx.params[1]) if want_bias else None
+        if ctx.needs_input_grad[1]:
+            tgt = _grad_target(ctx.params[0])
+            fold = want_bias and (tgt is None) == (tgt_b is None)
+            if fold:
+                gbias = tgt_b if tgt_b is not None else torch.empty(weight.shape[0], dtype=torch.float32, device=g.device)
+            with _wgrad_lane(tgt is not None, g, x):
+                gw = torch.zeros_like(weight) if tgt is None else tgt      # only the column block is written
+                wgrad(g, x, gw[:, c0:c1], accumulate=tgt is not None, bias_out=gbias if fold else None,
+                      bias_accumulate=tgt_b is not None)
+            if tgt is not None:
+                gw = None
+            if fold:
+                want_bias = False
+                if tgt_b is not None:
+                    gbias = None
+        if want_bias:
+            with _wgrad_lane(tgt_b is not None, g):
+                gbias = colsum(g, out=tgt_b)
+            if tgt_b is not None:
+                gbias = None
+        if ctx.needs_input_grad[0]:
+            gx = dense(g, weight[:, c0:c1], transpose_w=True)
+        return gx, gw, gbias, (g if ctx.has_addend else None), None, None
+
+
+def linear_part(x, weight, c0, c1, bias=None, addend=None):
+    return _LinearPart.apply(x, weight, bias, addend, int(c0), int(c1))
+
+
+_PTT = {"enabled": False}
+
+
+def enable_project_then_transfer(flag=True):
+    """Opt in: NodeEdgeInt applies the column block of its first Linear that acts on the TRANSFERRED features before
+    the transfer whenever the layer is narrower than the dense-connection buffer (results equal to fp32 rounding,
+    not bit for bit: the summation order of the reference is [transfer, then Linear])."""
+    _PTT["enabled"] = bool(flag)
+
+
+def project_then_transfer_enabled():
+    return _PTT["enabled"]
+
+
 class _PolyConv(torch.autograd.Function):
     """out = sum_k T_k(x) W_k^T + b for one operator (lib/Hodge_Cheb_Conv.py:480-515 / :394-439).
     x is [R, width] (already flattened), inner = last-dim size the Linear layers act on."""

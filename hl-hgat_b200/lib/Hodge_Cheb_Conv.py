@@ -222,29 +222,29 @@ class NodeEdgeInt(nn.Module):
     def forward(self, x_t, x_s, par, D, nvalid=(None, None)):
         inc = _incidence_of(par)
         ln = _lanes.active()
-        if ln is not None and not self.only_att:
+        if not self.only_att:
+            s2t = lambda v: F_hl.edge_to_node(v, D, inc)        # (1/D) |B1| v      (:294)  # noqa: E731
+            t2s = lambda v: F_hl.node_to_edge(v, inc)           # |B1|^T v / 2      (:295)  # noqa: E731
+            if ln is None:
+                return _mlp(self.WV_Node, x_s, s2t, x_t, nvalid[0]), _mlp(self.WV_Edge, x_t, t2s, x_s, nvalid[1])
             # two-lane issue (lanes.py): the node MLP stays on the node lane, the edge MLP goes to the edge lane;
             # the transfers are the only place where a lane reads the other lane's features
             ln.exchange(node_tensors=(x_t,), edge_tensors=(x_s,))
-            x_t1 = _mlp(self.WV_Node, F_hl.edge_to_node(x_s, D, inc), x_t, nvalid[0])
+            x_t1 = _mlp(self.WV_Node, x_s, s2t, x_t, nvalid[0])
             with ln.edge_ctx():
-                x_s1 = _mlp(self.WV_Edge, F_hl.node_to_edge(x_t, inc), x_s, nvalid[1])
+                x_s1 = _mlp(self.WV_Edge, x_t, t2s, x_s, nvalid[1])
             return x_t1, x_s1
         if ln is not None:
             ln.to_node(x_s)                # the gate is computed on the node lane
         x_s2t = F_hl.edge_to_node(x_s, D, inc)
         x_t2s = F_hl.node_to_edge(x_t, inc)
-        if self.only_att:
-            k_t, k_s = self.WK_Node(x_t), self.WK_Edge(x_s)
-            name = self._sigma_name()
-            if name is None:        # arbitrary activation object: gate pre-activation through the kernel is not available
-                raise N.HlError("NodeEdgeInt(only_att=True) supports sigma = nn.Sigmoid() or nn.ReLU()")
-            a_t = F_hl.att_gate(self.WQ_Edge(x_s2t), self.WQ_Node(x_t), k_t, self.lambda_Node, name)
-            a_s = F_hl.att_gate(self.WQ_Node(x_t2s), self.WQ_Edge(x_s), k_s, self.lambda_Edge, name)
-            return a_t, a_s
-        x_t1 = _mlp(self.WV_Node, x_s2t, x_t, nvalid[0])
-        x_s1 = _mlp(self.WV_Edge, x_t2s, x_s, nvalid[1])
-        return x_t1, x_s1
+        k_t, k_s = self.WK_Node(x_t), self.WK_Edge(x_s)
+        name = self._sigma_name()
+        if name is None:        # arbitrary activation object: gate pre-activation through the kernel is not available
+            raise N.HlError("NodeEdgeInt(only_att=True) supports sigma = nn.Sigmoid() or nn.ReLU()")
+        a_t = F_hl.att_gate(self.WQ_Edge(x_s2t), self.WQ_Node(x_t), k_t, self.lambda_Node, name)
+        a_s = F_hl.att_gate(self.WQ_Node(x_t2s), self.WQ_Edge(x_s), k_s, self.lambda_Edge, name)
+        return a_t, a_s
 
 
 MSI = NodeEdgeInt
@@ -278,11 +278,20 @@ def _bn_relu(bn, x, slope=0.0, nvalid=None):
     return y
 
 
-def _mlp(seq, transferred, own, nvalid=None):
-    """Linear(cat[transferred, own]) -> BN -> ReLU -> Linear -> BN -> ReLU without materialising the
-    concat: the first Linear is split over its two column blocks (lib/Hodge_Cheb_Conv.py:307-308)."""
+def _mlp(seq, other, transfer, own, nvalid=None):
+    """Linear(cat[transfer(other), own]) -> BN -> ReLU -> Linear -> BN -> ReLU without materialising the
+    concat: the first Linear is split over its two column blocks (lib/Hodge_Cheb_Conv.py:307-308).  `other` are the
+    features of the other simplex order, `transfer` the linear map that brings them over (:294 / :295).  With
+    functional.enable_project_then_transfer() and a layer narrower than `other`, the column block acting on the
+    transferred features is applied BEFORE the transfer (it commutes with it: the transfer mixes rows, the weights
+    mix columns), so the transfer moves the layer width."""
     lin0, bn0, _, lin1, bn1, _ = seq
-    h = F_hl.linear(transferred, lin0.weight, lin0.bias, x2=own)
+    d = other.shape[1]
+    if F_hl.project_then_transfer_enabled() and lin0.out_features < d and lin0.out_features % 16 == 0 and d % 4 == 0:
+        t = transfer(F_hl.linear_part(other, lin0.weight, 0, d))
+        h = F_hl.linear_part(own, lin0.weight, d, lin0.weight.shape[1], lin0.bias, addend=t)
+    else:
+        h = F_hl.linear(transfer(other), lin0.weight, lin0.bias, x2=own)
     h = _bn_relu(bn0, h, 0.0, nvalid)
     h = F_hl.linear(h, lin1.weight, lin1.bias)
     return _bn_relu(bn1, h, 0.0, nvalid)

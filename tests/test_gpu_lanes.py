@@ -201,3 +201,32 @@ def test_weight_split_plan_replays_bit_identical():
     torch.cuda.synchronize()
     for x, y, z in zip(got, ref, first):
         assert torch.equal(x, y) and not torch.equal(x, z)
+
+
+def test_project_then_transfer_equals_reference_order():
+    """functional.enable_project_then_transfer: (1/D)|B1| (x_s W_a^T) + x_t W_b^T + b == [(1/D)|B1| x_s | x_t] W^T + b to
+    fp32 rounding -- predictions, loss, every parameter gradient (weights of the split Linear included) and the
+    BatchNorm running statistics; also under two-lane issue."""
+    torch.manual_seed(0)
+    b = batch_to(make_batch("zinc", 96, seed=9), DEV)
+    ctor = dict(CTOR, channels=[2, 2])
+    model = M.HL_HGCNN_zinc_dense_int3_pyr(**ctor).to(DEV).train()
+
+    def loss_of(m):
+        return torch.nn.functional.l1_loss(m(b, device=DEV), b.y)
+
+    ref = _run(model, loss_of, False)[0]
+    for use_lanes in (False, True):
+        H.enable_project_then_transfer(True)
+        try:
+            got = _run(model, loss_of, use_lanes)[0]
+        finally:
+            H.enable_project_then_transfer(False)
+        assert abs(float(got[0]) - float(ref[0])) < 1e-5 * max(1.0, abs(float(ref[0])))
+        scale = max(float(y.abs().max()) for y in ref[1] if y is not None)
+        for (n, _), x, y in zip(model.named_parameters(), got[1], ref[1]):
+            assert (x is None) == (y is None), n
+            if x is not None:
+                assert float((x - y).norm()) <= 1e-4 * float(y.norm()) + 1e-6 * scale * y.numel() ** 0.5, n
+        for x, y in zip(got[2], ref[2]):
+            assert torch.allclose(x.float(), y.float(), rtol=1e-4, atol=1e-6)
