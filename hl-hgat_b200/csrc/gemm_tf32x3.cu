@@ -357,7 +357,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
     if (MODE == 1 && TS && P.colsum_ws && blockIdx.y == 0) {
       const int m = m0 + (warp & 3) * 32 + lane;
-      if (m < P.M) P.colsum_ws[((int64_t)blockIdx.z * 2 + cg) * P.M + m] = csum;   // one plane per split and group
+      if (m < P.M) {                                                 // one plane per split and group
+        P.colsum_ws[((int64_t)blockIdx.z * 2 + cg) * P.M + m] = csum;
+        if (groups == 1) P.colsum_ws[((int64_t)blockIdx.z * 2 + 1) * P.M + m] = 0.f;
+      }
     }
     // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (= output rows)
     gm_mbar_wait(acc_bar, 0);
@@ -753,10 +756,15 @@ extern "C" int hl_wgrad_bias_tf32x3(const float* g, int64_t ld_g, const float* x
   const bool fold_bias = dbias && use_ts;
   float* cs_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) +
                                           align_up((size_t)splits * (size_t)fo * (size_t)fi * sizeof(float), 256));
-  P.colsum_ws = fold_bias ? cs_ws : nullptr; P.conv_groups = use_ts ? 2 : 1;
+  // two converter groups alternate over the ring stages: a group must meet every phase of the barriers it waits on, so
+  // the stage count has to be even (with 3 stages group 0 would see stage 0 at rounds 0, 2, 4, ... and a parity wait
+  // cannot tell round 2 from round 0)
+  static int max_groups = 0;
+  if (max_groups == 0) { const char* e = getenv("HL_WGRAD_GROUPS"); max_groups = e ? atoi(e) : 2; if (max_groups < 1 || max_groups > 2) max_groups = 2; }
+  P.colsum_ws = fold_bias ? cs_ws : nullptr; P.conv_groups = (use_ts && max_groups == 2 && stages % 2 == 0) ? 2 : 1;
   dim3 grid(mtiles, ntiles, splits);
   P.kb_first = 0;
-  if (use_ts) gemm_tf32x3_kernel<1, 1><<<grid, kGmThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
+  if (use_ts) gemm_tf32x3_kernel<1, 1><<<grid, 64 + P.conv_groups * kGmConvThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
   else gemm_tf32x3_kernel<1, 0><<<grid, 64 + kGmConvThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
   HL_LAUNCH_CHECK("gemm_tf32x3_kernel<wgrad>");
   const int64_t n = (int64_t)fo * fi;

@@ -409,7 +409,9 @@ def test_tcgen05_dense_fp32_parity(M, Nn, K):
     assert float((y.double() - refy).abs().max()) < 1e-4 * float(refy.abs().max())
 
 
-@pytest.mark.parametrize("R,fo,fi", [(1472, 256, 448), (1600, 256, 704), (24000, 64, 64), (3000, 128, 192), (700, 256, 32)])
+@pytest.mark.parametrize("R,fo,fi", [(1472, 256, 448), (1600, 256, 704), (24000, 64, 64), (3000, 128, 192), (700, 256, 32),
+                                     # 160 / 224 / 96-column tiles: 3-stage rings (odd: one converter group), long k-loops
+                                     (60000, 64, 160), (60000, 128, 224), (40000, 64, 288), (230000, 32, 32)])
 def test_tcgen05_wgrad_vs_fp64(R, fo, fi):
     torch.manual_seed(R)
     g, x = torch.randn(R, fo, device=DEV), torch.randn(R, fi, device=DEV)
