@@ -187,10 +187,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t round = (uint32_t)(kb / stages);
-        gm_mbar_wait(&empty_bar[s], (round & 1u) ^ 1u);
+      // ring position as running counters (stage, phase parity): an integer division by the runtime stage count per
+      // k-block sat on the serial path of each role
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == stages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
+        gm_mbar_wait(&empty_bar[s], ph ^ 1u);
         unsigned char* st = base + (size_t)s * stage_bytes;
         if (MODE == 0) {
           gm_mbar_arrive_expect_tx(&full_bar[s], a_bytes + 2 * b_bytes);
@@ -217,10 +219,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       // instruction descriptor: D=F32, A=B=TF32, K-major both, N = bn, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kGmBM >> 4) << 24) |
                              (MODE == 1 ? ((TS ? 0u : (1u << 15)) | (1u << 16)) : 0u);   // A from TMEM is always K-major
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t round = (uint32_t)(kb / stages);
-        gm_mbar_wait(&conv_bar[s], round & 1u);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == stages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
+        gm_mbar_wait(&conv_bar[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = gm_smem_u32(base + (size_t)s * stage_bytes);
         const uint32_t a_hi = st, a_lo = st + a_bytes, b_hi = st + b_off, b_lo = st + b_off + b_bytes;
@@ -267,10 +269,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int cg = (warp - 2) >> 2;                                  // converter group 0 / 1
     const int ct = (threadIdx.x - 64) & (kGmConvThreads - 1);       // 0..127 inside the group
     float csum = 0.f;                                               // wgrad TS: running sum of this thread's G column
+    int s = cg;                                                      // groups <= stages, and stages even when groups == 2
+    uint32_t ph = 0;
     for (int kb = cg; kb < num_kb; kb += groups) {
-      const int s = kb % stages;
-      const uint32_t round = (uint32_t)(kb / stages);
-      gm_mbar_wait(&full_bar[s], round & 1u);
+      if (kb != cg) {
+        s += groups;
+        if (s >= stages) { s -= stages; ph ^= 1u; }
+      }
+      gm_mbar_wait(&full_bar[s], ph);
       if (TS) {
         // thread = tile row = its own TMEM lane: un-swizzle the 128-byte row (16-byte chunk c sits at c ^ (row % 8)),
         // split, and store hi | lo as 2 x 32 columns of the stage's TMEM slot
