@@ -103,3 +103,19 @@ def test_lanes_are_inert_without_cuda_tensors():
     finally:
         lanes.enable_lanes(False)
     lanes.join()
+
+
+def test_split_desc_layout_matches_header():
+    """hl_split_desc (include/hlhgat.h) as bound by ctypes: 3 pointers, 2 int64, 4 int32 = 56 bytes at their natural
+    offsets -- functional.WeightSplitPlan uploads an array of these to the device as raw bytes."""
+    import ctypes as C
+    import re
+    from hlhgat_b200 import _native as N
+    d = N.SplitDesc
+    offs = {f: getattr(d, f).offset for f, _ in d._fields_}
+    assert offs == {"src": 0, "hi": 8, "lo": 16, "ld_src": 24, "ld_out": 32, "rows": 40, "cols": 44, "transpose": 48, "reserved": 52}
+    assert C.sizeof(d) == 56
+    header = open(os.path.join(ROOT, "include", "hlhgat.h")).read()
+    body = re.search(r"typedef struct hl_split_desc \{(.*?)\} hl_split_desc;", header, re.S).group(1)
+    names = re.findall(r"(\w+);", body)
+    assert names == [f for f, _ in d._fields_]           # same members in the same order as the C declaration
