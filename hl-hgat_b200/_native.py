@@ -137,6 +137,10 @@ def ptr(t):
 
 
 def require_cuda_f32(*tensors):
+    """All tensors CUDA fp32 and on the CURRENT device: every call is enqueued on `torch.cuda.current_stream()` and the
+    kernels' one-time configuration is looked up for the current device (one process per GPU; a model on `cuda:1`
+    needs `torch.cuda.set_device(1)` or a `with torch.cuda.device(1):` around its calls)."""
+    cur = None
     for t in tensors:
         if t is None:
             continue
@@ -144,6 +148,11 @@ def require_cuda_f32(*tensors):
             raise HlError("hlhgat_b200 ops run on CUDA tensors only (no CPU fallback)")
         if t.dtype != torch.float32:
             raise HlError(f"expected float32, got {t.dtype}")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise HlError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: run under "
+                          f"torch.cuda.device({t.device.index}) (kernels are enqueued on the current device's stream)")
 
 
 def row_major(t):

@@ -23,6 +23,30 @@ void count_launch();   // bumps the library-wide kernel launch counter (hl_launc
     if (_e != cudaSuccess) return hl::record_cuda_error(_e, name); \
   } while (0)
 
+// One-time PER-DEVICE configuration (cudaFuncSetAttribute and the SM count belong to a device, not to the process):
+// `need()` is true the first time it is called with a given device current.
+struct DeviceOnce {
+  bool done[64] = {};
+  bool need() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
+// multiprocessor count of the CURRENT device (cached per device)
+static inline int device_sm_count() {
+  static int cached[64] = {};
+  int d = 0, n = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return 148;
+  if (cached[d] > 0) return cached[d];
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || n <= 0) n = 148;
+  cached[d] = n;
+  return n;
+}
+
 static inline cudaStream_t as_stream(hl_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }

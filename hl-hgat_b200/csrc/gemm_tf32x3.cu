@@ -585,11 +585,10 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
     return 1;
   if (K2 > 0) { if (!make_map(&ma2, A2, M, K2, lda2, kGmBM)) return 1; }
   else ma2 = ma;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;                                     // the attribute is per device
+  if (configured.need()) {
     HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
   }
   GemmParams P;
   P.M = M; P.N = N; P.K = Ktot; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
@@ -749,11 +748,10 @@ extern "C" int hl_wgrad_bias_tf32x3(const float* g, int64_t ld_g, const float* x
   CUtensorMap mg, mx;
   if (use_ts ? !make_map(&mg, g, nrows, fo, ld_g, 32, kGmBM, false, true) : !make_map(&mg, g, nrows, fo, ld_g, 32, 32, true)) return 1;
   if (!make_map(&mx, x, nrows, fi, ld_x, 32, 32, true)) return 1;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
   }
   GemmParams P;
   P.M = fo; P.N = fi; P.K = nrows; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;

@@ -352,22 +352,14 @@ int launch_poly_spmm_staged(const hl_spmm_problem* probs, int n, int32_t width, 
     tiles += (probs[i].nrows + tile_rows - 1) / tile_rows;
   }
   for (int i = n; i <= HL_MAX_SPMM_PROBLEMS; ++i) b.tile_start[i] = tiles;
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (sm_count <= 0) sm_count = 148;
-  }
+  const int sm_count = device_sm_count();
   const int grid = tiles < sm_count ? tiles : sm_count;
   const size_t smem = sizeof(StagedSmem) + 128;
 #define HL_ST_CASE(E)                                                                                         \
   case E: {                                                                                                   \
-    static bool configured = false;                                                                           \
-    if (!configured) {                                                                                        \
+    static DeviceOnce configured;                                                                             \
+    if (configured.need())                                                                                    \
       cudaFuncSetAttribute(poly_spmm_staged_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      configured = true;                                                                                      \
-    }                                                                                                         \
     poly_spmm_staged_kernel<E><<<grid, kStThreads, smem, stream>>>(b, width, tile_rows, tiles, c0, c1, c2, c3); \
   } break;
   switch (epi) {

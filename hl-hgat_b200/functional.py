@@ -108,7 +108,12 @@ class accumulate_into_grads:
     existing dense fp32 `param.grad` (e.g. the views of parallel.FlatGradBucket) and hand autograd `None`
     for those inputs -- the same values autograd's own `grad.add_(new)` would leave there, without one extra
     elementwise launch per parameter.  Outside the context (and under `torch.autograd.grad`) gradients are
-    returned as usual."""
+    returned as usual.
+
+    With lanes enabled these kernels run on auxiliary streams and write into `param.grad` behind autograd's back
+    (its end-of-backward stream synchronisation does not cover them), so leaving the context JOINS the lanes:
+    after `with accumulate_into_grads(): loss.backward()` the current stream is ordered after every gradient
+    write and an all-reduce / optimizer step may follow directly."""
 
     def __enter__(self):
         self.prev = _BACKWARD_MODE["accumulate"]
@@ -117,6 +122,8 @@ class accumulate_into_grads:
 
     def __exit__(self, *a):
         _BACKWARD_MODE["accumulate"] = self.prev
+        if not self.prev:
+            _lanes.join()                      # free when nothing was issued on a side stream
 
 
 def _grad_target(p):
@@ -740,12 +747,16 @@ class Segments:
         if nrows is None:
             finite = idx[torch.isfinite(idx)] if is_float else idx
             nrows = int(finite.max().item()) + 1 if finite.numel() else 0
+        # ids the bucketing drops (+inf = edge inside a cluster, anything outside [0, nrows)) own nothing: -1, which
+        # the adjoint (hl_owner_gather) turns into a zero gradient row instead of reading g[owner] out of bounds
         if is_float:
             idx = idx.to(torch.float32)
-            owner = torch.where(torch.isfinite(idx), idx, torch.full_like(idx, -1.0)).to(torch.int32)
+            keep = torch.isfinite(idx) & (idx >= 0) & (idx < nrows)
+            owner = torch.where(keep, idx, torch.full_like(idx, -1.0)).to(torch.int32)
         else:
             idx = idx.to(torch.int64)
-            owner = idx.to(torch.int32)
+            keep = (idx >= 0) & (idx < nrows)
+            owner = torch.where(keep, idx, torch.full_like(idx, -1)).to(torch.int32)
         rowptr, members, _, _ = csr_from_coo(idx, None, None, nrows, tie=N.HL_TIE_POSITION, row_is_float=is_float)
         return cls(rowptr, members, owner, nrows, idx.numel())
 
@@ -803,6 +814,13 @@ class _BnAct(torch.autograd.Function):
         R, F = x.shape
         y = torch.empty((R, F), dtype=torch.float32, device=x.device)
         stats = torch.empty(2 * F, dtype=torch.float32, device=x.device)
+        if R == 0:                                  # e.g. a coarse level without edges: nothing to normalise
+            stats.zero_()
+            ctx.empty = True
+            ctx.mark_non_differentiable(stats)
+            ctx.set_materialize_grads(False)
+            return y, stats
+        ctx.empty = False
         nb = L.hl_bn_workspace(R, F)
         ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
         N.check(L.hl_bn_act_fwd(x.data_ptr(), ldx, R, F, N.ptr(gamma), N.ptr(beta), eps, slope,
@@ -820,6 +838,8 @@ class _BnAct(torch.autograd.Function):
     def backward(ctx, dy, _):
         if dy is None:
             return (None,) * 10
+        if ctx.empty:
+            return (torch.zeros_like(dy),) + (None,) * 9
         x, y, gamma, stats = ctx.saved_tensors
         L = N.lib()
         R, F = x.shape
@@ -835,9 +855,60 @@ class _BnAct(torch.autograd.Function):
                                 N.ptr(gamma), stats.data_ptr(), ctx.eps, ctx.slope, dx.data_ptr(), dx.stride(0),
                                 dgamma.data_ptr(), dbeta.data_ptr(), 1 if fused else 0, N.ptr(ctx.nvalid), ws.data_ptr(), nb,
                                 N.stream_ptr()), "hl_bn_act_bwd")
-        if fused:
-            dgamma = dbeta = None
+        if fused or ctx.params[0] is None:          # BatchNorm1d(affine=False): gamma / beta are not autograd inputs
+            dgamma = None
+        if fused or ctx.params[1] is None:
+            dbeta = None
         return dx, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+class _BnActEval(torch.autograd.Function):
+    """Inference-mode BatchNorm1d (+ activation): y = act((x - running_mean) rsqrt(running_var + eps) gamma + beta) through
+    hl_bn_apply with the running statistics in place of the batch statistics; the statistics are constants, so the
+    adjoint is hl_bn_bwd_apply with zero column sums (dx = gamma rstd dz) and hl_bn_bwd_sums for dgamma / dbeta."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, slope, nvalid):
+        N.require_cuda_f32(x, gamma, beta, running_mean, running_var)
+        L = N.lib()
+        x, ldx = N.row_major(x)
+        R, F = x.shape
+        y = torch.empty((R, F), dtype=torch.float32, device=x.device)
+        stats = torch.cat([running_mean.detach().reshape(-1), running_var.detach().reshape(-1)]).contiguous()
+        if R > 0:
+            N.check(L.hl_bn_apply(x.data_ptr(), ldx, R, F, N.ptr(gamma), N.ptr(beta), stats.data_ptr(), eps, slope,
+                                  y.data_ptr(), y.stride(0), N.ptr(nvalid), N.stream_ptr()), "hl_bn_apply")
+        ctx.eps, ctx.slope, ctx.nvalid = eps, slope, nvalid
+        ctx.has = (gamma is not None, beta is not None)
+        ctx.save_for_backward(x, y, gamma, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, gamma, stats = ctx.saved_tensors
+        L = N.lib()
+        R, F = x.shape
+        dy, lddy = N.row_major(dy)
+        dx = torch.empty((R, F), dtype=torch.float32, device=x.device)
+        if R == 0:
+            return dx, None, None, None, None, None, None, None
+        sums = torch.empty(2 * F, dtype=torch.float32, device=x.device)
+        zeros = torch.zeros(2 * F, dtype=torch.float32, device=x.device)
+        one = torch.ones(1, dtype=torch.float32, device=x.device)
+        nb = L.hl_bn_workspace(R, F)
+        ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+        N.check(L.hl_bn_bwd_sums(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), dy.data_ptr(), lddy, R, F,
+                                 stats.data_ptr(), ctx.eps, ctx.slope, sums.data_ptr(), N.ptr(ctx.nvalid), ws.data_ptr(), nb,
+                                 N.stream_ptr()), "hl_bn_bwd_sums")
+        N.check(L.hl_bn_bwd_apply(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), dy.data_ptr(), lddy, R, F,
+                                  N.ptr(gamma), stats.data_ptr(), zeros.data_ptr(), one.data_ptr(), ctx.eps, ctx.slope,
+                                  dx.data_ptr(), dx.stride(0), N.ptr(ctx.nvalid), N.stream_ptr()), "hl_bn_bwd_apply")
+        return dx, (sums[F:] if ctx.has[0] else None), (sums[:F] if ctx.has[1] else None), None, None, None, None, None
+
+
+def bn_act_eval(x, gamma, beta, running_mean, running_var, eps=1e-5, slope=0.0, nvalid=None):
+    """Inference-mode BatchNorm1d over rows + (leaky) ReLU (slope = 1: no activation) with the running statistics."""
+    return _BnActEval.apply(x, gamma, beta, running_mean, running_var, float(eps), float(slope), nvalid)
 
 
 class _SyncBnAct(torch.autograd.Function):
@@ -897,6 +968,10 @@ class _SyncBnAct(torch.autograd.Function):
             tg.add_(dgamma)
             tb.add_(dbeta)
             dgamma = dbeta = None
+        if ctx.params[0] is None:
+            dgamma = None
+        if ctx.params[1] is None:
+            dbeta = None
         return dx, dgamma, dbeta, None, None, None, None
 
 

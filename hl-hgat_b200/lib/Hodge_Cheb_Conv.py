@@ -38,7 +38,7 @@ class _GlorotLinear(nn.Module):
             self.weight.uniform_(-a, a)
 
     def forward(self, x):
-        return torch.matmul(x, self.weight.t())
+        return F_hl.linear(x.reshape(-1, x.shape[-1]), self.weight).view(*x.shape[:-1], -1)
 
 
 class _HodgePolyConv(nn.Module):
@@ -103,13 +103,27 @@ class HodgeLaguerreFastConv(_HodgePolyConv):
         return _fastconv_quirk(x, ws, self.bias, op)
 
 
-class _QuirkBasis(torch.autograd.Function):
-    """T_1 = x - A x, T_{k+1} = (-A x + (2k+1) T_k - k T_{k-1})/(k+1): one SpMM, the rest elementwise
-    inside the SpMM epilogues (xg = x for every order)."""
+def _quirk_coefficients(K):
+    """With DEMO :561 every order k >= 2 propagates the ORIGINAL x, so T_k = a_k x + b_k (A x) with
+    T_0 = x, T_1 = x - A x, T_{k+1} = (-A x + (2k+1) T_k - k T_{k-1}) / (k+1)."""
+    a, b = [1.0, 1.0], [0.0, -1.0]
+    for k in range(1, K - 1):
+        a.append(((2 * k + 1) * a[k] - k * a[k - 1]) / (k + 1))
+        b.append(((2 * k + 1) * b[k] - k * b[k - 1] - 1.0) / (k + 1))
+    return a[:K], b[:K]
+
+
+class _QuirkConv(torch.autograd.Function):
+    """out = sum_k T_k W_k^T + b with the quirk basis (DEMO lib/Hodge_Cheb_Conv.py:542-578).  Forward: the basis through
+    the SpMM recurrence epilogues in the reference's evaluation order (xg = x for every order), the Theta transforms on
+    the tcgen05 GEMM.  Backward: weight gradients g^T T_k on the tensor-core weight-gradient kernel; since T_k = a_k x +
+    b_k A x, dx = g (sum_k a_k W_k) + A^T (g (sum_k b_k W_k)): two GEMMs and one adjoint SpMM."""
 
     @staticmethod
-    def forward(ctx, x, op, K):
-        x = x.contiguous()
+    def forward(ctx, x, bias, op, inner, *weights):
+        N.require_cuda_f32(x, bias, *weights)
+        K = len(weights)
+        x = x.contiguous()                       # [R, T*C]: A acts on rows, the Theta transforms on the last `inner` columns
         ts = [x]
         for k in range(K - 1):
             if k == 0:
@@ -117,39 +131,40 @@ class _QuirkBasis(torch.autograd.Function):
             else:
                 ts.append(F_hl.poly_spmm(op.fwd, op.nrows, x, N.HL_EPI_LAGUERRE_STEP, c=(float(k), 0, 0, 0),
                                          p1=ts[k], p2=ts[k - 1]))
-        ctx.op, ctx.K = op, K
-        return tuple(ts[1:])
+        v = [t.view(-1, inner) for t in ts]
+        out = F_hl.dense2(v[0], weights[0], v[1], weights[1], bias)
+        for k in range(2, K, 2):
+            if k + 1 < K:
+                F_hl.dense2(v[k], weights[k], v[k + 1], weights[k + 1], None, out=out, accumulate=True)
+            else:
+                F_hl.dense(v[k], weights[k], None, out=out, accumulate=True)
+        ctx.op, ctx.has_bias, ctx.inner = op, bias is not None, inner
+        ctx.save_for_backward(*ts, *weights)
+        return out
 
     @staticmethod
-    def backward(ctx, *gs):
-        K, op = ctx.K, ctx.op
-        # S_k (k>=1) = G_k + b_k S_{k+1} + c_{k+1} S_{k+2};  dx = b_0 S_1 + c_1 S_2 + A^T sum_k a_k S_{k+1}
-        S = [None] * (K + 2)
-        acc = None
-        for k in range(K - 1, 0, -1):
-            s = gs[k - 1].clone()
-            if S[k + 1] is not None:
-                s = s + (2.0 * k + 1.0) / (k + 1) * S[k + 1]
-            if S[k + 2] is not None:
-                s = s - (k + 1.0) / (k + 2) * S[k + 2]
-            S[k] = s
-            a = -1.0 if k == 1 else -1.0 / k          # a_{k-1}
-            acc = a * s if acc is None else acc + a * s
-        own = S[1].clone()
-        if S[2] is not None:
-            own = own - 0.5 * S[2]
-        dx = F_hl.poly_spmm(op.bwd, op.nrows, acc.contiguous(), N.HL_EPI_LINCOMB, c=(1.0, 1.0, 0, 0), p1=own)
-        return dx, None, None
+    def backward(ctx, g):
+        K = len(ctx.saved_tensors) // 2
+        ts, weights = ctx.saved_tensors[:K], ctx.saved_tensors[K:]
+        op, inner = ctx.op, ctx.inner
+        g = g.contiguous()
+        gb = F_hl.colsum(g) if ctx.has_bias and ctx.needs_input_grad[1] else None
+        gws = [F_hl.wgrad(g, ts[k].view(-1, inner)) if ctx.needs_input_grad[4 + k] else None for k in range(K)]
+        gx = None
+        if ctx.needs_input_grad[0]:
+            a, b = _quirk_coefficients(K)
+            wa = sum(ak * w for ak, w in zip(a, weights))            # [Fout, Fin] weight-sized combinations
+            wb = sum(bk * w for bk, w in zip(b, weights))
+            own = F_hl.dense(g, wa.contiguous(), transpose_w=True).view(ts[0].shape)
+            acc = F_hl.dense(g, wb.contiguous(), transpose_w=True).view(ts[0].shape)
+            gx = F_hl.poly_spmm(op.bwd, op.nrows, acc, N.HL_EPI_LINCOMB, c=(1.0, 1.0, 0, 0), p1=own)
+        return (gx, gb, None, None, *gws)
 
 
 def _fastconv_quirk(x, ws, bias, op):
     shp = x.shape
-    xf = x.reshape(shp[0], -1)
-    ts = _QuirkBasis.apply(xf, op, len(ws))
-    out = torch.matmul(x, ws[0].t())
-    for k in range(1, len(ws)):
-        out = out + torch.matmul(ts[k - 1].view(shp), ws[k].t())
-    return out + bias if bias is not None else out
+    out = _QuirkConv.apply(x.reshape(shp[0], -1), bias, op, shp[-1], *ws)
+    return out.view(*shp[:-1], -1)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -238,12 +253,13 @@ class NodeEdgeInt(nn.Module):
             ln.to_node(x_s)                # the gate is computed on the node lane
         x_s2t = F_hl.edge_to_node(x_s, D, inc)
         x_t2s = F_hl.node_to_edge(x_t, inc)
-        k_t, k_s = self.WK_Node(x_t), self.WK_Edge(x_s)
+        proj = lambda lin, v: F_hl.linear(v, lin.weight, lin.bias)        # Q / K projections (:297-302) on the tcgen05 GEMM  # noqa: E731
+        k_t, k_s = proj(self.WK_Node, x_t), proj(self.WK_Edge, x_s)
         name = self._sigma_name()
         if name is None:        # arbitrary activation object: gate pre-activation through the kernel is not available
             raise N.HlError("NodeEdgeInt(only_att=True) supports sigma = nn.Sigmoid() or nn.ReLU()")
-        a_t = F_hl.att_gate(self.WQ_Edge(x_s2t), self.WQ_Node(x_t), k_t, self.lambda_Node, name)
-        a_s = F_hl.att_gate(self.WQ_Node(x_t2s), self.WQ_Edge(x_s), k_s, self.lambda_Edge, name)
+        a_t = F_hl.att_gate(proj(self.WQ_Edge, x_s2t), proj(self.WQ_Node, x_t), k_t, self.lambda_Node, name)
+        a_s = F_hl.att_gate(proj(self.WQ_Node, x_t2s), proj(self.WQ_Edge, x_s), k_s, self.lambda_Edge, name)
         return a_t, a_s
 
 
@@ -254,9 +270,8 @@ def _bn_relu(bn, x, slope=0.0, nvalid=None):
     """nn.BatchNorm1d (+ReLU) through the fused kernels in training mode; running statistics updated
     exactly like torch (momentum, unbiased variance).  `nvalid` (device int32 scalar) marks the rows
     beyond it as padding of a fixed-capacity batch."""
-    if not (bn.training or not bn.track_running_stats):
-        y = torch.nn.functional.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
-        return torch.nn.functional.leaky_relu(y, slope) if slope != 1.0 else y
+    if not (bn.training or not bn.track_running_stats):      # eval(): the running statistics, same apply kernel
+        return F_hl.bn_act_eval(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, slope, nvalid)
     track = bn.track_running_stats and bn.training
     if track:
         counter = bn.num_batches_tracked

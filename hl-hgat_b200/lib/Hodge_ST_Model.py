@@ -33,7 +33,7 @@ class _MlpBlock(nn.Sequential):
 
     def forward(self, x, nvalid=None):
         lin, bn, _, drop = self
-        return drop(_bn_relu(bn, lin(x), 0.0, nvalid))
+        return drop(_bn_relu(bn, F_hl.linear(x, lin.weight, lin.bias), 0.0, nvalid))
 
 
 class HL_HGCNN_zinc_dense_int3_pyr(nn.Module):

@@ -7,6 +7,8 @@ COO in `propagate`, `par.abs()` re-coalescing in `NodeEdgeInt`, lib/Hodge_Cheb_C
 transpose) by `hl_csr_from_coo`, cached on the identity of the incoming tensors, and every
 layer of the model reuses them.
 """
+import weakref
+
 import torch
 
 from . import _native as N
@@ -131,39 +133,49 @@ class Incidence:
 
 
 # ---------------------------------------------------------------------------------------------
-# identity-keyed caches: the unchanged reference models re-pass the same COO tensors to every
-# layer and rebuild B1 at every stage (lib/Hodge_ST_Model.py:623-624); conversion happens once.
+# per-tensor caches: the unchanged reference models re-pass the same COO tensors to every layer and
+# rebuild B1 at every stage (lib/Hodge_ST_Model.py:623-624); conversion happens once per mini-batch.
+# The built tables hang off the SOURCE tensor (`edge_index._hl_ops`), so they live exactly as long as
+# the batch they belong to -- nothing global keeps operators of earlier mini-batches resident in HBM.
 # ---------------------------------------------------------------------------------------------
-_OP_CACHE = {}
-_CACHE_LIMIT = 64
+_ATTACHED = weakref.WeakSet()        # tensors carrying an `_hl_ops` table (for clear_caches)
 
 
-def _key(*tensors):
-    return tuple((t.data_ptr(), tuple(t.shape), t._version) for t in tensors if t is not None)
+def _table(t):
+    tab = getattr(t, "_hl_ops", None)
+    if tab is None:
+        tab = t._hl_ops = {}
+        _ATTACHED.add(t)
+    return tab
 
 
-def _put(cache, key, value, keep):
-    if len(cache) >= _CACHE_LIMIT:
-        cache.pop(next(iter(cache)))
-    cache[key] = (value, keep)        # `keep` pins the source tensors so data_ptr stays unique
-    return value
+def _sig(t):
+    return None if t is None else (t.data_ptr(), tuple(t.shape), t._version)
 
 
 def operator_for(edge_index, edge_weight, nrows):
-    key = ("op", nrows) + _key(edge_index, edge_weight)
-    hit = _OP_CACHE.get(key)
-    if hit is not None:
-        return hit[0]
-    return _put(_OP_CACHE, key, CsrOperator(edge_index, edge_weight, nrows), (edge_index, edge_weight))
+    tab = _table(edge_index)
+    key = ("op", nrows, _sig(edge_index), _sig(edge_weight))
+    op = tab.get(key)
+    if op is None:
+        tab.clear()                   # an in-place update of the COO (new `_version`) invalidates what was built from it
+        op = tab[key] = CsrOperator(edge_index, edge_weight, nrows)
+    return op
 
 
 def incidence_for(edge_index, num_nodes):
-    key = ("inc", num_nodes) + _key(edge_index)
-    hit = _OP_CACHE.get(key)
-    if hit is not None:
-        return hit[0]
-    return _put(_OP_CACHE, key, Incidence(edge_index, num_nodes), (edge_index,))
+    tab = _table(edge_index)
+    key = ("inc", num_nodes, _sig(edge_index))
+    inc = tab.get(key)
+    if inc is None:
+        for k in [k for k in tab if k[0] == "inc"]:
+            del tab[k]
+        inc = tab[key] = Incidence(edge_index, num_nodes)
+    return inc
 
 
 def clear_caches():
-    _OP_CACHE.clear()
+    """Forget every table built so far (the static buffers of a captured step change content between replays, and the
+    rebuild has to be part of the capture)."""
+    for t in list(_ATTACHED):
+        t._hl_ops.clear()
