@@ -378,8 +378,15 @@ def test_staged_kernel_equals_per_row_kernel_fwd_and_bwd(width, K):
         for a, c in zip(res[(1, fam)], res[(0, fam)]):
             for u, v in zip(a, c):
                 assert torch.equal(u, v), (fam, float((u - v).abs().max()))
-    # and the adjoint really is the adjoint: <A x, y> == <x, A^T y> through the K=2 Laguerre pair
-    x, y = xs[1].double(), g0[1].double()
+    # and the adjoint really is the adjoint: with zero incoming gradient on T_0, the K=2 Laguerre pair gives
+    # T_1 = x - A x and dx = G_1 - A^T G_1, so <T_1(x), G_1> == <x, dx> (in fp64 accumulation of fp32 results)
+    for op, x, g in zip(ops, xs, gt):
+        (t,) = F_hl.poly_basis_fwd(N.HL_LAGUERRE, 2, [op], [x], width)
+        a0, a1 = torch.zeros_like(x), g[:1].clone()
+        F_hl.poly_basis_bwd(N.HL_LAGUERRE, 2, [op], [a0], [a1], width)
+        lhs = float((t[0].double() * g[0].double()).sum())
+        rhs = float((x.double() * a0.double()).sum())
+        assert abs(lhs - rhs) < 1e-5 * max(1.0, abs(lhs), float(t[0].double().norm() * g[0].double().norm()) * 1e-2), (lhs, rhs)
 
 
 @pytest.mark.parametrize("M,Nn,K", [(300, 64, 64), (24001, 256, 704), (5000, 128, 28), (777, 32, 100), (1000, 512, 64),
