@@ -72,8 +72,9 @@ def test_tsp_reference_protocol_on_b200_ops_vs_golden():
 
 
 def test_protocol_equals_mirrored_model_classes():
-    """The mirrored model classes (hlhgat_b200.lib.Hodge_ST_Model: operators bucketed once, no gnn.Sequential) and the
-    reference protocol compute the same function: forward bit for bit on the same weights."""
+    """The mirrored model classes (hlhgat_b200.lib.Hodge_ST_Model: operators bucketed once, fused BatchNorm + ReLU kernels,
+    no gnn.Sequential) and the reference protocol (torch BatchNorm1d / ReLU between the B200 operators) compute the same
+    function on the same weights, to fp32 rounding."""
     from hlhgat_b200.lib.Hodge_ST_Model import HL_HGCNN_zinc_dense_int3_pyr
     from hlhgat_b200.synthetic import make_batch, batch_to
     torch.manual_seed(0)
@@ -82,4 +83,4 @@ def test_protocol_equals_mirrored_model_classes():
     b = ZincPyrProtocol(OPS, gnn, degree, **ctor).to(DEV).train()
     b.load_state_dict(a.state_dict(), strict=True)
     d = batch_to(make_batch("zinc", 48, seed=5), DEV)
-    assert torch.equal(a(d, device=DEV), b(d, device=DEV))
+    close(a(d, device=DEV), b(d, device=DEV), rtol=1e-5, atol=1e-5)
