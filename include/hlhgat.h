@@ -279,6 +279,29 @@ int hl_bn_bwd_apply(const float* x, int64_t ld_x, const float* y, int64_t ld_y, 
                     const int32_t* nvalid, hl_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Eigenvector positional encodings of every graph of a mini-batch.
+ * Replaces: `eig_pe(L, k)` = scipy.linalg.eigh of the dense normalised Laplacian + argsort + columns 1 .. k-1
+ * (lib/Hodge_Dataset.py:97-112; callers :457-458 ZINC, :586-587 peptides, :846-847 CIFAR10SP) and the dense `eigh`
+ * behind it, per graph on the CPU.  The diagonal blocks of a block-diagonal CSR operator (rows seg_ptr[g] ..
+ * seg_ptr[g+1] of `rowptr / colidx / vals`, e.g. L0 or L1 from hl_laplacian_fill or hl_csr_from_coo) are expanded
+ * into dense scratch and diagonalised by one CTA each (cyclic Jacobi, round-robin pair order, fp32).
+ *   evals[R]          eigenvalues of every block in ascending order (R = seg_ptr[n_graphs])
+ *   pe[R, k-1]        eigenvectors of rank 1 .. k-1 (rank 0, the constant vector of a connected graph, is skipped like
+ *                     the reference's `eig_vecs[:, 1:k]`); blocks with fewer than k rows are zero-padded, which is what
+ *                     the datasets' `get` does (:430-431); sign: largest-magnitude component positive (the reference
+ *                     inherits LAPACK's arbitrary sign and re-draws it at random per sample, :429-439)
+ *   vecs_all          optional (nullable): all eigenvectors, [n_g, n_g] row-major per block at mat_ptr[g]
+ *   sweeps            optional (nullable): Jacobi sweeps used per block
+ * mat_ptr[g] = sum_{h<g} n_h^2 (int64, device), total_matrix_elements = mat_ptr[n_graphs] (host), max_n = max n_g.
+ * -------------------------------------------------------------------------------------------- */
+size_t hl_eig_pe_workspace(int64_t total_matrix_elements);
+int hl_eig_pe(const int32_t* seg_ptr, int32_t n_graphs, int32_t max_n, const int64_t* mat_ptr,
+              int64_t total_matrix_elements, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+              int32_t k, float* evals, float* pe, int64_t ld_pe, float* vecs_all /* nullable */,
+              int32_t* sweeps /* nullable */, int32_t max_sweeps, void* workspace, size_t workspace_bytes,
+              hl_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
  * Greedy heavy-edge matching for multi-level graph coarsening, one warp per graph of the mini-batch.
  * Nodes are visited in id order; an unmatched node u pairs with its unmatched neighbour of largest edge_weight
  * (NULL = all ones; ties: first in ascending incident-edge order); cluster[u] = cluster[partner] = u.

@@ -583,3 +583,21 @@ class HL_HGCNN_pepfunc_dense_int3_attpool(_AttPoolBase):
                 par, D, ei_t, ew_t, ei_s, ew_s = self._level(datas, 1, x_t0, x_s0)
         out = self._head(self._readout(datas, x_t, x_s, len(self.channels) - 1))
         return (out, att_t, att_s) if if_att else out
+
+
+# --------------------------------------------------------------------------------------
+# eigenvector positional encodings (lib/Hodge_Dataset.py:97-112)
+# --------------------------------------------------------------------------------------
+def eig_pe(L, k=9):
+    """`eig_pe` of the reference: scipy.linalg.eigh of the dense matrix, columns reordered by ascending eigenvalue,
+    eigenvectors 1 .. k-1 (the first one -- the constant vector of a connected graph's Laplacian -- is dropped)."""
+    import numpy as np
+    from scipy.linalg import eigh
+    vals, vecs = eigh(L.numpy() if torch.is_tensor(L) else L)
+    vecs = np.real(vecs[:, vals.argsort()])
+    return torch.from_numpy(vecs[:, 1:k])
+
+
+def dense_operator(edge_index, edge_weight, n, dtype=torch.float32):
+    """The dense matrix `dense_to_sparse` was applied to (row-major COO -> dense)."""
+    return torch.zeros(n, n, dtype=dtype).index_put_((edge_index[0], edge_index[1]), edge_weight.to(dtype), accumulate=True)
