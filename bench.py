@@ -234,6 +234,8 @@ def run_ours(args, world, rank, local):
     F_hl.enable_factored_hodge1(factored)
     hlhgat_b200.enable_lanes(args.lanes == "on")
     hlhgat_b200.enable_project_then_transfer(args.project_first == "on")
+    from hlhgat_b200.dense_stack import enable_dense_stack
+    enable_dense_stack(args.dense_stack == "on")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     torch.manual_seed(0)
@@ -321,6 +323,9 @@ def run_ours(args, world, rank, local):
                                     f"to a fixed capacity ({cap_txt}, ~2% ghost rows), then all-reduce + fused Adam graph"
                                     + ("; node chain and edge chain of every layer on two streams = two parallel branches of the graph"
                                        if args.lanes == "on" else ""),
+                       "dense_connections": ("preallocated [rows, width] buffers: BatchNorm writes each block in place, each block transferred once, "
+                                             "data gradients accumulated by the GEMM epilogue (forward bit-identical to cat + re-transfer)"
+                                             if args.dense_stack == "on" else "torch.cat per layer + whole concat re-transferred (the reference's scheme)"),
                        "transfer": ("project-then-transfer in NodeEdgeInt: (1/D)|B1| (x W_a^T) instead of ((1/D)|B1| x) W_a^T"
                                     if args.project_first == "on" else "transfer-then-project (the reference's order)"),
                        "edge_operator": ("L1 applied in factored form diag(2/lambda) B1^T B1 (opt-in, fp32-rounding-equal to the CSR path)"
@@ -413,6 +418,9 @@ def main():
     ap.add_argument("--project-first", default="off", choices=["on", "off"],
                     help="NodeEdgeInt applies W_a before the node<->edge transfer when the layer is narrower than the "
                          "dense-connection buffer (transfers move f instead of d columns; fp32-rounding-equal)")
+    ap.add_argument("--dense-stack", default="on", choices=["on", "off"],
+                    help="dense connections in preallocated buffers (no torch.cat, every block transferred to the other simplex "
+                         "order once, data gradients accumulated in the GEMM epilogue); off = the reference's cat + full re-transfer")
     ap.add_argument("--factored-l1", default="auto", choices=["auto", "on", "off"],
                     help="apply the edge Laplacian as diag(2/lambda) B1^T B1 instead of its CSR; auto = only for the long-row "
                          "workloads (cifar, tsp); the ZINC headline always uses the CSR SpMM")

@@ -7,6 +7,7 @@ from .build import build  # noqa: F401
 from . import simplex, functional, lanes  # noqa: F401
 from .lanes import enable_lanes  # noqa: F401
 from .functional import enable_project_then_transfer  # noqa: F401
+from .dense_stack import enable_dense_stack  # noqa: F401
 from .lib.Hodge_Cheb_Conv import (HodgeLaguerreConv, HodgeChebConv, HodgeLaguerreFastConv,  # noqa: F401
                                   NodeEdgeInt, MSI, SAPool, HL_filter, NEConv, GraphBatchNorm,
                                   adj2par1, degree)

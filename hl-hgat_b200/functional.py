@@ -807,12 +807,15 @@ def segment_mean(src, seg, scale=None):
 # ---------------------------------------------------------------------------------------------
 class _BnAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, slope, nvalid, running_mean, running_var, momentum, counter=None):
+    def forward(ctx, x, gamma, beta, eps, slope, nvalid, running_mean, running_var, momentum, counter=None, tap=None):
         N.require_cuda_f32(x, gamma, beta)
         L = N.lib()
         x, ldx = N.row_major(x)
         R, F = x.shape
-        y = torch.empty((R, F), dtype=torch.float32, device=x.device)
+        # tap = (stack, side, c0, c1): the output is block [c0, c1) of a dense-connection buffer (dense_stack.DenseStack),
+        # written in place there, and the backward pass picks the block's gradient up from the stack's accumulator
+        ctx.tap = tap
+        y = torch.empty((R, F), dtype=torch.float32, device=x.device) if tap is None else tap[0].target(*tap[1:])[0]
         stats = torch.empty(2 * F, dtype=torch.float32, device=x.device)
         if R == 0:                                  # e.g. a coarse level without edges: nothing to normalise
             stats.zero_()
@@ -836,10 +839,12 @@ class _BnAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _):
+        if ctx.tap is not None:
+            dy = ctx.tap[0].collect("own", *ctx.tap[1:], dy)
         if dy is None:
-            return (None,) * 10
+            return (None,) * 11
         if ctx.empty:
-            return (torch.zeros_like(dy),) + (None,) * 9
+            return (torch.zeros_like(dy),) + (None,) * 10
         x, y, gamma, stats = ctx.saved_tensors
         L = N.lib()
         R, F = x.shape
@@ -859,7 +864,7 @@ class _BnAct(torch.autograd.Function):
             dgamma = None
         if fused or ctx.params[1] is None:
             dbeta = None
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
 class _BnActEval(torch.autograd.Function):
@@ -993,9 +998,9 @@ def bn_act_train_synced(x, gamma, beta, group, eps=1e-5, slope=0.0, nvalid=None,
 
 
 def bn_act_train(x, gamma, beta, eps=1e-5, slope=0.0, nvalid=None, running_mean=None, running_var=None, momentum=0.1,
-                 counter=None):
+                 counter=None, tap=None):
     """Training-mode BatchNorm1d over rows + (leaky) ReLU; returns (y, stats[2F] = mean | biased var).
     `nvalid`: optional device int32 scalar -- rows beyond it are padding (excluded, written as zeros).
     running_mean / running_var (optional) are updated in the same launch, like nn.BatchNorm1d; `counter`
     (optional int64 scalar: num_batches_tracked) is incremented there too."""
-    return _BnAct.apply(x, gamma, beta, float(eps), float(slope), nvalid, running_mean, running_var, momentum, counter)
+    return _BnAct.apply(x, gamma, beta, float(eps), float(slope), nvalid, running_mean, running_var, momentum, counter, tap)

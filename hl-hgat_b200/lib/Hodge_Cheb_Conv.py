@@ -13,6 +13,7 @@ from torch import Tensor
 from torch.nn import Parameter
 
 from .. import functional as F_hl
+from .. import dense_stack as _ds
 from .. import lanes as _lanes
 from .. import parallel as _parallel
 from .. import _native as N
@@ -266,12 +267,47 @@ class NodeEdgeInt(nn.Module):
 MSI = NodeEdgeInt
 
 
-def _bn_relu(bn, x, slope=0.0, nvalid=None):
+def _mlp_stack(seq, stack, side, d, nvalid=None):
+    """`_mlp` reading [transferred | own] in place from the dense-connection buffers of `stack`."""
+    lin0, bn0, _, lin1, bn1, _ = seq
+    h = _ds.stack_linear(stack, side, d, lin0.weight, lin0.bias)
+    h = _bn_relu(bn0, h, 0.0, nvalid)
+    h = F_hl.linear(h, lin1.weight, lin1.bias)
+    return _bn_relu(bn1, h, 0.0, nvalid)
+
+
+def node_edge_int_on_stack(module, stack, nvalid=(None, None)):
+    """`NodeEdgeInt.forward(x_t0, x_s0, par, D)` (value path, lib/Hodge_Cheb_Conv.py:293-309) with x_t0 / x_s0 living in
+    a `DenseStack`: only the blocks appended since the last call are transferred (each exactly once), the rest of
+    `(1/D)|B1| x_s0` / `|B1|^T x_t0 / 2` is already in the stack's transfer buffers."""
+    assert not module.only_att
+    if isinstance(stack, _ds.CatStack):
+        return module(stack.x["t"], stack.x["s"], stack.inc, stack.D, nvalid)
+    ln = _lanes.active()
+    d = stack.cols
+    if ln is not None:
+        c0, c1, x_t, x_s = stack.blocks[-1]
+        ln.exchange(node_tensors=(x_t,), edge_tensors=(x_s,))
+    stack.transfer_pending("t")
+    x_t1 = _mlp_stack(module.WV_Node, stack, "t", d, nvalid[0])
+    with (ln.edge_ctx() if ln is not None else contextlib.nullcontext()):
+        stack.transfer_pending("s")
+        x_s1 = _mlp_stack(module.WV_Edge, stack, "s", d, nvalid[1])
+    return x_t1, x_s1
+
+
+def _into(tap, y):
+    """A block computed into its own tensor -> its slice of the dense-connection buffer (copied in)."""
+    return y if tap is None else _ds._Publish.apply(y, *tap)
+
+
+def _bn_relu(bn, x, slope=0.0, nvalid=None, tap=None):
     """nn.BatchNorm1d (+ReLU) through the fused kernels in training mode; running statistics updated
     exactly like torch (momentum, unbiased variance).  `nvalid` (device int32 scalar) marks the rows
-    beyond it as padding of a fixed-capacity batch."""
+    beyond it as padding of a fixed-capacity batch.  `tap` = (stack, side, c0, c1): the output is written
+    straight into that block of a dense-connection buffer (dense_stack.DenseStack)."""
     if not (bn.training or not bn.track_running_stats):      # eval(): the running statistics, same apply kernel
-        return F_hl.bn_act_eval(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, slope, nvalid)
+        return _into(tap, F_hl.bn_act_eval(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, slope, nvalid))
     track = bn.track_running_stats and bn.training
     if track:
         counter = bn.num_batches_tracked
@@ -288,8 +324,8 @@ def _bn_relu(bn, x, slope=0.0, nvalid=None):
     group = _parallel.sync_batchnorm_group()
     if group is not False:                    # opt-in: statistics over all data-parallel ranks (parallel.enable_sync_batchnorm)
         y, _ = F_hl.bn_act_train_synced(x, bn.weight, bn.bias, group, bn.eps, slope, nvalid, rm, rv, m, counter)
-    else:
-        y, _ = F_hl.bn_act_train(x, bn.weight, bn.bias, bn.eps, slope, nvalid, rm, rv, m, counter)
+        return _into(tap, y)
+    y, _ = F_hl.bn_act_train(x, bn.weight, bn.bias, bn.eps, slope, nvalid, rm, rv, m, counter, tap)
     return y
 
 
@@ -323,8 +359,8 @@ class GraphBatchNorm(nn.Module):
     def forward(self, x):
         return _bn_relu(self.module, x, slope=1.0)
 
-    def forward_act(self, x, slope=0.0, nvalid=None):
-        return _bn_relu(self.module, x, slope, nvalid)
+    def forward_act(self, x, slope=0.0, nvalid=None, tap=None):
+        return _bn_relu(self.module, x, slope, nvalid, tap)
 
 
 class NEConv(nn.Module):
@@ -340,15 +376,33 @@ class NEConv(nn.Module):
         self.module_5 = GraphBatchNorm(fout)
         self.slope, self.p = slope, dropout_ratio
 
-    def forward(self, x_t, edge_index_t, edge_weight_t, x_s, edge_index_s, edge_weight_s, nvalid=(None, None)):
+    def forward(self, x_t, edge_index_t, edge_weight_t, x_s, edge_index_s, edge_weight_s, nvalid=(None, None), stack=None):
+        """`stack` (dense_stack.DenseStack, optional): the outputs become the next block of the dense-connection
+        buffers -- the BatchNorm kernel writes them there directly (the `torch.cat` of lib/Hodge_ST_Model.py:632-633)."""
         ln = _lanes.active()
-        x_t = self.module_1.forward_act(self.module_0(x_t, edge_index_t, edge_weight_t), self.slope, nvalid[0])
+        drop = self.p > 0.0 and self.training
+        taps = (None, None)
+        cat = isinstance(stack, _ds.CatStack)
+        if stack is not None and not cat:
+            c0, c1 = stack.reserve(self.module_1.module.num_features)
+            taps = ((stack, "t", c0, c1), (stack, "s", c0, c1))
+        x_t = self.module_1.forward_act(self.module_0(x_t, edge_index_t, edge_weight_t), self.slope, nvalid[0],
+                                        None if drop else taps[0])
         if self.p > 0.0:
             x_t = torch.nn.functional.dropout(x_t, self.p, self.training)
+            if drop:
+                x_t = _into(taps[0], x_t)
         with (ln.edge_ctx() if ln is not None else contextlib.nullcontext()):   # x_s lives on the edge lane (lanes.py)
-            x_s = self.module_5.forward_act(self.module_4(x_s, edge_index_s, edge_weight_s), self.slope, nvalid[1])
+            x_s = self.module_5.forward_act(self.module_4(x_s, edge_index_s, edge_weight_s), self.slope, nvalid[1],
+                                            None if drop else taps[1])
             if self.p > 0.0:
                 x_s = torch.nn.functional.dropout(x_s, self.p, self.training)
+                if drop:
+                    x_s = _into(taps[1], x_s)
+        if cat:
+            stack.publish(x_t, x_s)
+        elif stack is not None:
+            stack.commit(c0, c1, x_t, x_s)
         return [x_t, x_s]
 
 

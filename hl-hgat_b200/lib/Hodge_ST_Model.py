@@ -8,8 +8,9 @@ import torch.nn as nn
 
 from .. import functional as F_hl
 from .. import lanes as _lanes
+from ..dense_stack import new_stack
 from ..simplex import Hodge1Factor, incidence_for, operator_for
-from .Hodge_Cheb_Conv import NEConv, NodeEdgeInt, adj2par1, degree, _bn_relu
+from .Hodge_Cheb_Conv import NEConv, NodeEdgeInt, adj2par1, degree, _bn_relu, node_edge_int_on_stack
 
 
 def _share_tables(ln, op_s, inc):
@@ -78,20 +79,18 @@ class HL_HGCNN_zinc_dense_int3_pyr(nn.Module):
         if D is None:
             D = inc.degree()                # = degree(edge_index.view(-1)) of :624 (no 1e-6 in this model)
         with _lanes.open_lanes(x_t.device) as ln:      # ln is None unless lanes.enable_lanes(): single stream
-            edge = ln.edge_ctx if ln is not None else contextlib.nullcontext
             _share_tables(ln, op_s, inc)
-            x_t, x_s = self.HL_init_conv(x_t, op_t, None, x_s, op_s, None, nv)
-            x_s0, x_t0 = x_s, x_t
             last = (len(self.channels) - 1, self.channels[-1] - 1)
+            # dense connections in preallocated buffers: no torch.cat, every block transferred once (dense_stack.py);
+            # the block of the last layer is never read (:627-636) and stays out of the buffers
+            width = self.initial_channel + sum(f * c for f, c in zip(self.filters, self.channels)) - self.filters[-1]
+            stack = new_stack(n, e, width, inc, D, x_t.device)
+            x_t, x_s = self.HL_init_conv(x_t, op_t, None, x_s, op_s, None, nv, stack=stack)
             for i, _ in enumerate(self.channels):
                 for j in range(self.channels[i]):
-                    x_t, x_s = getattr(self, f"NEInt{i}{j}")(x_t0, x_s0, inc, D, nv)
-                    x_t, x_s = getattr(self, f"NEConv{i}{j}")(x_t, op_t, None, x_s, op_s, None, nv)
-                    if (i, j) == last:
-                        break              # the dense-connection buffers of the last layer are never read (:627-636)
-                    x_t0 = torch.cat([x_t0, x_t], dim=-1)
-                    with edge():
-                        x_s0 = torch.cat([x_s0, x_s], dim=-1)
+                    x_t, x_s = node_edge_int_on_stack(getattr(self, f"NEInt{i}{j}"), stack, nv)
+                    x_t, x_s = getattr(self, f"NEConv{i}{j}")(x_t, op_t, None, x_s, op_s, None, nv,
+                                                              stack=None if (i, j) == last else stack)
             if ln is not None:
                 ln.to_node(x_s)
         x = torch.cat((F_hl.segment_mean(x_s, seg_s), F_hl.segment_mean(x_t, seg_t)), -1)
@@ -144,25 +143,31 @@ class _Level:
                 F_hl.Segments.from_counts(torch.as_tensor(d.num_edge1, device=dev), total=self.e))
 
 
-def _stage(self, i, lv, x_t0, x_s0):
-    """One stage of NEInt / NEConv layers with dense connections.  With lanes enabled (lanes.py) the edge chain is
-    issued on the edge lane; the stage hands everything back to the node lane at its end (gates, pooling and
-    the head run there)."""
+def _stage(self, i, lv, stack, keep_last=True):
+    """One stage of NEInt / NEConv layers with dense connections held in `stack` (dense_stack.py).  With lanes enabled
+    (lanes.py) the edge chain is issued on the edge lane; the stage hands everything back to the node lane at its end
+    (gates, pooling and the head run there).  keep_last=False: the block of the stage's last layer is not appended
+    (nothing reads the buffers afterwards)."""
     x_t = x_s = None
     ln = _lanes.active()
-    edge = ln.edge_ctx if ln is not None else contextlib.nullcontext
     if ln is not None:
         _share_tables(ln, lv.op_s, lv.inc)
-        ln.to_edge(x_s0)
-    for j in range(self.channels[i]):
-        x_t, x_s = getattr(self, f"NEInt{i}{j}")(x_t0, x_s0, lv.inc, lv.D, lv.nv)
-        x_t, x_s = getattr(self, f"NEConv{i}{j}")(x_t, lv.op_t, None, x_s, lv.op_s, None, lv.nv)
-        x_t0 = torch.cat([x_t0, x_t], dim=-1)
-        with edge():
-            x_s0 = torch.cat([x_s0, x_s], dim=-1)
+        ln.edge.wait_stream(ln.node)
+    nl = self.channels[i]
+    for j in range(nl):
+        x_t, x_s = node_edge_int_on_stack(getattr(self, f"NEInt{i}{j}"), stack, lv.nv)
+        x_t, x_s = getattr(self, f"NEConv{i}{j}")(x_t, lv.op_t, None, x_s, lv.op_s, None, lv.nv,
+                                                  stack=stack if (keep_last or j + 1 < nl) else None)
     if ln is not None:
-        ln.to_node(x_s, x_s0)
-    return x_t, x_s, x_t0, x_s0
+        ln.to_node(x_s)
+    return x_t, x_s
+
+
+def _stack_width(self, first, stages, drop_last):
+    """Columns a stack needs: `first` (its initial block) + the layers of `stages`, minus the very last block if
+    nothing reads the buffers after it."""
+    w = first + sum(self.channels[i] * self.filters[i] for i in stages)
+    return w - (self.filters[stages[-1]] if drop_last and stages else 0)
 
 
 class _SeqConv(nn.Module):
@@ -208,10 +213,11 @@ class HL_HGCNN_TSP_dense_int3_pyr(nn.Module):
         lv = _Level(data, x_t.shape[0], x_s.shape[0], 1e-6, x_t.device)
         with _lanes.open_lanes(x_t.device) as ln:
             _share_tables(ln, lv.op_s, lv.inc)
-            x_t, x_s = self.HL_init_conv(x_t, lv.op_t, None, x_s, lv.op_s, None, lv.nv)
-            x_t0, x_s0 = x_t, x_s
-            for i, _ in enumerate(self.channels):
-                x_t, x_s, x_t0, x_s0 = _stage(self, i, lv, x_t0, x_s0)
+            stages = list(range(len(self.channels)))
+            stack = new_stack(lv.n, lv.e, _stack_width(self, self.initial_channel, stages, True), lv.inc, lv.D, x_t.device)
+            x_t, x_s = self.HL_init_conv(x_t, lv.op_t, None, x_s, lv.op_s, None, lv.nv, stack=stack)
+            for i in stages:
+                x_t, x_s = _stage(self, i, lv, stack, keep_last=i != stages[-1])
         x_s = torch.cat([x_s, F_hl.boundary_absdiff(x_t, lv.inc)], dim=-1)
         if len(self.mlp_channels) == 1:
             x_s = self.mlp(x_s, lv.op_s, lv.nv[1])
@@ -272,19 +278,23 @@ class HL_HGCNN_CIFAR10SP_dense_int3_attpool(_AttPool):
         seg_pt, seg_ps = self._positions(datas, lv, n1, e1, dev)
         with _lanes.open_lanes(dev) as ln:
             _share_tables(ln, lv.op_s, lv.inc)
-            x_t, x_s = self.HL_init_conv(d0.x_t[:, 1:], lv.op_t, None, d0.x_s[:, 1:], lv.op_s, None, lv.nv)
-            x_t0, x_s0 = x_t, x_s
+            ns = len(self.channels)
+            before, after = list(range(self.pool_loc + 1)), list(range(self.pool_loc + 1, ns))
+            stack = new_stack(lv.n, lv.e, _stack_width(self, self.initial_channel, before, False), lv.inc, lv.D, dev)
+            x_t, x_s = self.HL_init_conv(d0.x_t[:, 1:], lv.op_t, None, d0.x_s[:, 1:], lv.op_s, None, lv.nv, stack=stack)
             att_t = att_s = None
-            for i, _ in enumerate(self.channels):
-                x_t, x_s, x_t0, x_s0 = _stage(self, i, lv, x_t0, x_s0)
+            for i in range(ns):
+                x_t, x_s = _stage(self, i, lv, stack, keep_last=i == self.pool_loc or i != ns - 1)
                 if i == self.pool_loc:
                     att_t, att_s = getattr(self, "NEAtt%d" % i)(x_t, x_s, lv.inc, lv.D)
                     att_t = att_t / att_t.max()
                     att_s = att_s / att_s.max()
                     x_t, x_s = x_t * att_t, x_s * att_s
-                    x_t0 = F_hl.segment_mean(x_t0, seg_pt)
-                    x_s0 = F_hl.segment_mean(x_s0, seg_ps)
+                    x_t0 = F_hl.segment_mean(stack.whole("t"), seg_pt)
+                    x_s0 = F_hl.segment_mean(stack.whole("s"), seg_ps)
                     lv = _Level(d1, n1, e1, 1e-6, dev)
+                    stack = new_stack(n1, e1, _stack_width(self, x_t0.shape[1], after, True), lv.inc, lv.D, dev)
+                    stack.publish(x_t0, x_s0)
         x = self._head(x_t, x_s, lv)
         if if_final_layer:
             return x, self.out(x)
@@ -319,20 +329,28 @@ class HL_HGCNN_pepfunc_dense_int3_attpool(_AttPool):
         seg_pt, seg_ps = self._positions(datas, lv, n1, e1, dev)
         with _lanes.open_lanes(dev) as ln:
             _share_tables(ln, lv.op_s, lv.inc)
-            x_t, x_s = self.HL_init_conv(d0.x_t[:, 1:], lv.op_t, None, d0.x_s[:, 1:], lv.op_s, None, lv.nv)
-            x_t0, x_s0 = x_t, x_s
             last = len(self.channels) - 1
+            # the sigmoid gate rescales the WHOLE dense-connection buffer after every stage (:131-134), so every stage
+            # starts a fresh stack from the gated (and, at pool_loc, pooled) buffers
+            stack = new_stack(lv.n, lv.e, _stack_width(self, self.initial_channel, [0], last == 0 and not if_att), lv.inc, lv.D, dev)
+            x_t, x_s = self.HL_init_conv(d0.x_t[:, 1:], lv.op_t, None, d0.x_s[:, 1:], lv.op_s, None, lv.nv, stack=stack)
             for i, _ in enumerate(self.channels):
-                x_t, x_s, x_t0, x_s0 = _stage(self, i, lv, x_t0, x_s0)
+                x_t, x_s = _stage(self, i, lv, stack, keep_last=i != last or if_att)
                 if i == last and not if_att:
                     break                      # the last gate only rescales buffers nothing reads (:131-134 then :150)
+                x_t0, x_s0 = stack.whole("t"), stack.whole("s")
                 att_t, att_s = getattr(self, "NEAtt%d" % i)(x_t0, x_s0, lv.inc, lv.D)
+                if i == last:
+                    break
                 if i == self.pool_loc:
                     x_t0 = F_hl.segment_mean(x_t0, seg_pt, att_t)
                     x_s0 = F_hl.segment_mean(x_s0, seg_ps, att_s)
                     lv = _Level(d1, n1, e1, 1e-6, dev)
-                elif i != last:
+                else:
                     x_t0, x_s0 = x_t0 * att_t, x_s0 * att_s
+                stack = new_stack(lv.n, lv.e, _stack_width(self, x_t0.shape[1], [i + 1], i + 1 == last and not if_att),
+                                  lv.inc, lv.D, dev)
+                stack.publish(x_t0, x_s0)
         x = self._head(x_t, x_s, lv)
         if if_att:
             return self.out(x), att_t, att_s
