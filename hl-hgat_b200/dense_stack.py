@@ -143,9 +143,11 @@ class DenseStack:
 
     def collect(self, kind, side, c0, c1, g):
         """Total gradient of block [c0, c1): what the stack consumers accumulated (if any) plus autograd's `g`."""
-        if self.consumed[(kind, side)] < c1:
+        # `filled`: leading columns some consumer's backward has written.  A consumer whose output did not reach the loss
+        # (e.g. the gate of the last stage when only the prediction is trained) never runs and leaves no gradient here;
+        # the autograd engine runs every consumer that does BEFORE the producer of the block (they are its graph children)
+        if self.filled[(kind, side)] < c1:
             return g
-        assert self.filled[(kind, side)] >= c1, "a stack consumer of this block has not run its backward yet"
         sl = _alias(self._gbuf(kind, side), c0, c1)
         if g is not None:
             sl.add_(g)

@@ -284,7 +284,7 @@ int hl_bn_bwd_apply(const float* x, int64_t ld_x, const float* y, int64_t ld_y, 
  * (lib/Hodge_Dataset.py:97-112; callers :457-458 ZINC, :586-587 peptides, :846-847 CIFAR10SP) and the dense `eigh`
  * behind it, per graph on the CPU.  The diagonal blocks of a block-diagonal CSR operator (rows seg_ptr[g] ..
  * seg_ptr[g+1] of `rowptr / colidx / vals`, e.g. L0 or L1 from hl_laplacian_fill or hl_csr_from_coo) are expanded
- * into dense scratch and diagonalised by one CTA each (cyclic Jacobi, round-robin pair order, fp32).
+ * into dense fp64 scratch and diagonalised by one CTA each (cyclic Jacobi, round-robin pair order).
  *   evals[R]          eigenvalues of every block in ascending order (R = seg_ptr[n_graphs])
  *   pe[R, k-1]        eigenvectors of rank 1 .. k-1 (rank 0, the constant vector of a connected graph, is skipped like
  *                     the reference's `eig_vecs[:, 1:k]`); blocks with fewer than k rows are zero-padded, which is what

@@ -1,7 +1,8 @@
 """eigenvector positional encodings (lib/Hodge_Dataset.py:97-112) as a batched GPU
 eigensolver.  Eigenvectors are only defined up to sign (and up to a rotation inside a degenerate eigenspace), so parity
 is stated on invariants:
-  * eigenvalues equal the fp64 LAPACK ones (atol 2e-6 on operators with spectrum in [0, 2]);
+  * eigenvalues equal the fp64 LAPACK ones (atol 1e-6 on operators with spectrum in [0, 2]: the iteration runs in fp64,
+    only the output is rounded to fp32);
   * every returned column is an eigenvector: ||L v - lambda v|| <= 5e-6, and the columns are orthonormal (1e-5);
   * for an isolated eigenvalue the column equals the reference's up to sign: | |v| - |v_ref| | <= 1e-4;
   * for a cluster of (near-)equal eigenvalues that lies wholly inside the returned range the orthogonal PROJECTOR onto
@@ -27,11 +28,17 @@ def _clusters(vals, tol):
     return groups
 
 
+def _vec_tol(w, a):
+    """An fp32 eigensolver (the reference's scipy call on float32 input) perturbs an eigenvector by ~ eps32 * ||L|| / gap."""
+    gap = min(w[a] - w[a - 1] if a > 0 else np.inf, w[a + 1] - w[a] if a + 1 < len(w) else np.inf)
+    return 1e-5 + 4e-6 / gap
+
+
 def check_against_dense(pe, evals, L64, k, gap=2e-3):
     """pe [n, k-1], evals [n] from the GPU against the dense fp64 matrix L64 [n, n]."""
     n = L64.shape[0]
     w, U = np.linalg.eigh(L64)
-    assert np.abs(evals - w).max() < 2e-6 * max(1.0, np.abs(w).max()), np.abs(evals - w).max()
+    assert np.abs(evals - w).max() < 1e-6 * max(1.0, np.abs(w).max()), np.abs(evals - w).max()
     cols = min(k, n) - 1
     V = pe[:, :cols].astype(np.float64)
     assert np.abs(pe[:, cols:]).max(initial=0.0) == 0.0                                 # zero padding for n < k
@@ -48,8 +55,7 @@ def check_against_dense(pe, evals, L64, k, gap=2e-3):
         elif a >= 1 and b <= cols + 1:                                                  # whole cluster returned: compare projectors
             P, Pref = V[:, a - 1:b - 1] @ V[:, a - 1:b - 1].T, U[:, a:b] @ U[:, a:b].T
             assert np.abs(P - Pref).max() < 1e-4
-    big = np.abs(V).argmax(0)
-    assert (V[big, np.arange(cols)] > 0).all()                                          # the sign convention
+    assert (V.max(0) >= -V.min(0) - 1e-6).all()                                         # sign convention: largest |component| positive
 
 
 def test_oracle_eig_pe_matches_reference_output_in_fixtures():
@@ -64,7 +70,7 @@ def test_oracle_eig_pe_matches_reference_output_in_fixtures():
             w = np.linalg.eigvalsh(L)
             for a, b in _clusters(w, 2e-3):
                 if b - a == 1 and a >= 1:                                               # isolated: equal up to sign
-                    assert np.abs(np.abs(mine[:, a - 1].numpy()) - np.abs(x[:, raw + a - 1].numpy())).max() < 1e-4
+                    assert np.abs(np.abs(mine[:, a - 1].numpy()) - np.abs(x[:, raw + a - 1].numpy())).max() < _vec_tol(w, a)
 
 
 @pytest.mark.gpu
@@ -93,8 +99,8 @@ def test_gpu_eig_pe_vs_reference_fixtures_and_lapack():
             ref = g["x_" + side][:, raw:].numpy()                                       # the reference's own eig_pe columns
             w = np.linalg.eigvalsh(L)
             for a, b in _clusters(w, 2e-3):
-                if b - a == 1 and 1 <= a < min(k, m):
-                    assert np.abs(np.abs(pe[r:r + m, a - 1]) - np.abs(ref[:, a - 1])).max() < 1e-4
+                if b - a == 1 and 1 <= a < min(k, m):                               # vs the reference's fp32 LAPACK vectors
+                    assert np.abs(np.abs(pe[r:r + m, a - 1]) - np.abs(ref[:, a - 1])).max() < _vec_tol(w, a)
             r += m
 
 
