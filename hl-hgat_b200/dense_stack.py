@@ -109,6 +109,14 @@ class DenseStack:
         own = [b[2] if side == "t" else b[3] for b in self.blocks]
         return own + list(self.tr_blocks[side])
 
+    def close(self):
+        """End of the forward pass over this stack: drop the references to the block tensors.  They were only held to
+        name them as inputs of later consumers; keeping them would close a reference cycle (block -> grad_fn -> ctx ->
+        stack -> block) that keeps the whole autograd graph of a step -- and the AccumulateGrad nodes of the parameters,
+        with the stream they were created on -- alive until the garbage collector runs."""
+        self.blocks = []
+        self.tr_blocks = {"t": [], "s": []}
+
     def whole(self, side):
         """The dense-connection buffer of `side` as one autograd tensor [rows, cols] (for gates, pooling, heads)."""
         return _StackView.apply(self, side, self.cols, *[b[2] if side == "t" else b[3] for b in self.blocks])
@@ -173,6 +181,9 @@ class CatStack:
 
     def whole(self, side):
         return self.x[side]
+
+    def close(self):
+        pass
 
 
 def new_stack(n_t, n_s, width, inc, D, device):

@@ -91,6 +91,7 @@ class HL_HGCNN_zinc_dense_int3_pyr(nn.Module):
                     x_t, x_s = node_edge_int_on_stack(getattr(self, f"NEInt{i}{j}"), stack, nv)
                     x_t, x_s = getattr(self, f"NEConv{i}{j}")(x_t, op_t, None, x_s, op_s, None, nv,
                                                               stack=None if (i, j) == last else stack)
+            stack.close()
             if ln is not None:
                 ln.to_node(x_s)
         x = torch.cat((F_hl.segment_mean(x_s, seg_s), F_hl.segment_mean(x_t, seg_t)), -1)
@@ -218,6 +219,7 @@ class HL_HGCNN_TSP_dense_int3_pyr(nn.Module):
             x_t, x_s = self.HL_init_conv(x_t, lv.op_t, None, x_s, lv.op_s, None, lv.nv, stack=stack)
             for i in stages:
                 x_t, x_s = _stage(self, i, lv, stack, keep_last=i != stages[-1])
+            stack.close()
         x_s = torch.cat([x_s, F_hl.boundary_absdiff(x_t, lv.inc)], dim=-1)
         if len(self.mlp_channels) == 1:
             x_s = self.mlp(x_s, lv.op_s, lv.nv[1])
@@ -293,8 +295,10 @@ class HL_HGCNN_CIFAR10SP_dense_int3_attpool(_AttPool):
                     x_t0 = F_hl.segment_mean(stack.whole("t"), seg_pt)
                     x_s0 = F_hl.segment_mean(stack.whole("s"), seg_ps)
                     lv = _Level(d1, n1, e1, 1e-6, dev)
+                    stack.close()
                     stack = new_stack(n1, e1, _stack_width(self, x_t0.shape[1], after, True), lv.inc, lv.D, dev)
                     stack.publish(x_t0, x_s0)
+            stack.close()
         x = self._head(x_t, x_s, lv)
         if if_final_layer:
             return x, self.out(x)
@@ -337,8 +341,10 @@ class HL_HGCNN_pepfunc_dense_int3_attpool(_AttPool):
             for i, _ in enumerate(self.channels):
                 x_t, x_s = _stage(self, i, lv, stack, keep_last=i != last or if_att)
                 if i == last and not if_att:
+                    stack.close()
                     break                      # the last gate only rescales buffers nothing reads (:131-134 then :150)
                 x_t0, x_s0 = stack.whole("t"), stack.whole("s")
+                stack.close()
                 att_t, att_s = getattr(self, "NEAtt%d" % i)(x_t0, x_s0, lv.inc, lv.D)
                 if i == last:
                     break
