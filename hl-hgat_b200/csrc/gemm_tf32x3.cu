@@ -368,13 +368,19 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (groups == 1) P.colsum_ws[((int64_t)blockIdx.z * 2 + 1) * P.M + m] = 0.f;
       }
     }
-    // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (= output rows)
+    // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (= output rows).  Each 32-column chunk goes TMEM -> registers
+    // (thread = row) -> a padded per-warp staging tile in shared memory (the ring is idle by now) -> global memory with
+    // 8 lanes per row, so a warp instruction moves four complete 128-byte row segments (full sectors) instead of 32
+    // half-filled ones; in accumulate mode the old values are fetched the same way and BEFORE the tcgen05.ld wait.
     gm_mbar_wait(acc_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float* Cbase = P.C + (MODE == 1 ? (int64_t)blockIdx.z * P.split_stride : 0);
     const int quad = warp & 3;
     const int row = m0 + quad * 32 + lane;
     const bool vec_ok = (P.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
+    constexpr int kPitch = 36;                                        // floats per staged row: 144 B, conflict-free for 16-byte accesses
+    float* stage_tile = reinterpret_cast<float*>(base) + (size_t)(warp - 2) * 32 * kPitch;
+    const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;          // coalesced phase: 4 rows x 8 float4 per instruction
     for (int c = 32 * cg; c < bn; c += 32 * groups) {                // the groups take alternate 32-column chunks
       uint32_t r[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c;
@@ -388,33 +394,52 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr)
           : "memory");
+      if (vec_ok) {
+        const int col = n0 + c + sub_col;
+        const bool col_ok = col + 3 < P.N && c + sub_col < bn;
+        float4 old[8];
+        if (P.accumulate) {                                           // independent loads, in flight under the TMEM read
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = m0 + quad * 32 + it * 4 + sub_row;
+            old[it] = (col_ok && rr < P.M) ? *reinterpret_cast<const float4*>(Cbase + (int64_t)rr * P.ldc + col)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (P.bias && col_ok) {
+          if ((reinterpret_cast<uintptr_t>(P.bias) & 15) == 0) bv = __ldg(reinterpret_cast<const float4*>(P.bias + col));
+          else bv = make_float4(__ldg(P.bias + col), __ldg(P.bias + col + 1), __ldg(P.bias + col + 2), __ldg(P.bias + col + 3));
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float* mine = stage_tile + lane * kPitch;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(mine + j) =
+              num_kb > 0 ? make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int lr = it * 4 + sub_row;
+          const int rr = m0 + quad * 32 + lr;
+          float4 v = *reinterpret_cast<const float4*>(stage_tile + lr * kPitch + sub_col);
+          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          if (P.accumulate) { v.x += old[it].x; v.y += old[it].y; v.z += old[it].z; v.w += old[it].w; }
+          if (col_ok && rr < P.M) *reinterpret_cast<float4*>(Cbase + (int64_t)rr * P.ldc + col) = v;
+        }
+        __syncwarp();                                                 // the staging tile is reused by the next chunk
+        continue;
+      }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < P.M) {
+      if (row < P.M) {                                                // unaligned output: element-wise
         float* crow = Cbase + (int64_t)row * P.ldc + n0 + c;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < 32; ++j) {
           const int col = n0 + c + j;
-          if (col >= P.N || c + j >= bn) break;                   // tile overhang / columns past this CTA's bn
-          float v[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) v[t] = num_kb > 0 ? __uint_as_float(r[j + t]) : 0.f;
-          if (P.bias) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-              if (col + t < P.N) v[t] += __ldg(P.bias + col + t);
-          }
-          if (vec_ok && col + 3 < P.N) {
-            float4* dst = reinterpret_cast<float4*>(crow + j);
-            if (P.accumulate) {
-              const float4 o = *dst;
-              v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
-            }
-            *dst = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-              if (col + t < P.N) crow[j + t] = P.accumulate ? crow[j + t] + v[t] : v[t];
-          }
+          if (col >= P.N || c + j >= bn) break;                    // tile overhang / columns past this CTA's bn
+          float v = num_kb > 0 ? __uint_as_float(r[j]) : 0.f;
+          if (P.bias) v += __ldg(P.bias + col);
+          crow[j] = P.accumulate ? crow[j] + v : v;
         }
       }
     }
