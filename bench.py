@@ -141,26 +141,15 @@ def run_reference(args, world, rank):
     line = {"impl": "reference", "metric": wl.metric, "value": gps, "unit": "graphs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl.label, "note": "CPU: pure-torch restatement of the "
-                       "reference (PyG not installable), not PyG itself"},
+            "config": {"workload": wl.label, "graphs_per_gpu": sample, "global_batch": sample,
+                       "note": "CPU: pure-torch restatement of the reference (PyG not installable), not PyG itself"},
             "cpu_baseline": {"value": gps, "unit": "graphs/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} training steps on {sample}-graph batches "
-                                       f"(a bounded sample of the {wl.batch}-graph workload), {cores} torch threads"},
+                             "sample": (f"{args.steps} training steps on full {sample}-graph batches (the workload's own batch size), "
+                                        if sample == wl.batch else
+                                        f"{args.steps} training steps on {sample}-graph batches (a bounded sample of the "
+                                        f"{wl.batch}-graph workload), ") + f"{cores} torch threads"},
             "e2e": {"value": gps, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=_OUT, flush=True)
-
-
-def ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the SpMM launch from the committed ncu capture."""
-    try:
-        tot = 0.0
-        for ln in open(os.path.join(ROOT, "profiles", "r1_spmm_v3_staged_full.txt")):
-            if ln.startswith("dram__bytes_read.sum") or ln.startswith("dram__bytes_write.sum"):
-                val, unit = ln.split("=")[1].split()[:2]
-                tot += float(val) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
-        return tot or None
-    except Exception:
-        return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -172,46 +161,94 @@ ROOFLINE_CASES = {
 }
 
 
-def spmm_roofline(dev, batch_dev, workload="zinc", iters=20):
-    """Fused L0+L1 launch (HL_EPI_LAGUERRE_FIRST: T_1 = x - A x, the first SpMM of every conv) on the bench
-    batch replicated `reps` times block-diagonally so that x and T_1 exceed the 126 MB L2."""
-    from hlhgat_b200 import functional as F_hl, _native as N
-    from hlhgat_b200.simplex import CsrOperator
-    reps, width = ROOFLINE_CASES[workload]
-    ops, xs, nnz_tot, rows_tot = [], [], 0, 0
-    for ei, ew, r in ((batch_dev.edge_index_t, batch_dev.edge_weight_t, batch_dev.x_t.shape[0]),
-                      (batch_dev.edge_index_s, batch_dev.edge_weight_s, batch_dev.x_s.shape[0])):
-        off = (torch.arange(reps, device=dev) * r).repeat_interleave(ei.shape[1])
-        big_ei = ei.repeat(1, reps) + off
-        op = CsrOperator(big_ei, ew.repeat(reps), r * reps)
-        op.fwd
-        ops.append(op)
-        xs.append(torch.randn(r * reps, width, device=dev))
-        nnz_tot += big_ei.shape[1]
-        rows_tot += r * reps
-    alg_bytes = 8 * nnz_tot + 4 * (rows_tot + 2) + 4 * rows_tot * width * 2          # n_in = 1 (x), n_out = 1 (T_1)
+def _time_launch(fn, iters):
     for _ in range(3):
-        F_hl.poly_basis_fwd(N.HL_LAGUERRE, 2, ops, xs, width)
+        fn()
     torch.cuda.synchronize()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
     for a, b in evs:
         a.record()
-        F_hl.poly_basis_fwd(N.HL_LAGUERRE, 2, ops, xs, width)
+        fn()
         b.record()
     torch.cuda.synchronize()
-    ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+    return statistics.mean(a.elapsed_time(b) for a, b in evs)
+
+
+def spmm_roofline(dev, batch_dev, workload="zinc", factored=False, iters=20):
+    """The polynomial SpMM launch of the step (HL_EPI_LAGUERRE_FIRST: T_1 = x - A x, the first SpMM of every conv) in two
+    regimes: on the bench batch replicated `reps` times block-diagonally so that x and T_1 exceed the 126 MB L2 (the
+    roofline figure), and on the bench batch itself (`in_step`: what a launch inside the timed step sees -- operator and
+    features L2-resident).  CSR workloads: the fused L0+L1 launch.  `factored` (cifar / tsp): the edge operator is applied
+    as diag(2/lambda) B1^T (B1 x) by hodge1_node_kernel + hodge1_edge_kernel -- THOSE launches are timed, against their
+    own algorithmic bytes."""
+    from hlhgat_b200 import functional as F_hl, _native as N
+    from hlhgat_b200.simplex import CsrOperator, Hodge1Factor, incidence_for
+    reps, width = ROOFLINE_CASES[workload]
     pk, kind = peaks()
+
+    def build(rep):
+        ops, xs, nnz_tot, rows_tot = [], [], 0, 0
+        n0, e0 = batch_dev.x_t.shape[0], batch_dev.x_s.shape[0]
+        for ei, ew, r in ((batch_dev.edge_index_t, batch_dev.edge_weight_t, n0), (batch_dev.edge_index_s, batch_dev.edge_weight_s, e0)):
+            off = (torch.arange(rep, device=dev) * r).repeat_interleave(ei.shape[1])
+            op = CsrOperator(ei.repeat(1, rep) + off, ew.repeat(rep), r * rep)
+            op.fwd
+            ops.append(op)
+            xs.append(torch.randn(r * rep, width, device=dev))
+            nnz_tot += ei.shape[1] * rep
+            rows_tot += r * rep
+        if factored:                                      # the edge operator in factored form: its own launches, its own bytes
+            und = batch_dev.edge_index
+            off = (torch.arange(rep, device=dev) * n0).repeat_interleave(und.shape[1])
+            inc = incidence_for(und.repeat(1, rep) + off, n0 * rep)
+            ops[1].factored = Hodge1Factor.from_operator(ops[1], inc)
+            n, e = n0 * rep, e0 * rep
+            node_pass = 4 * (n + 1) + 16 * e + 4 * width * (e + n)
+            edge_pass = 12 * e + 4 * width * (n + e * (1 + 1))        # n_epi = 1: the own-row x of T_1 = x - A x
+            return [ops[1]], [xs[1]], node_pass + edge_pass, e, nnz_tot
+        alg = 8 * nnz_tot + 4 * (rows_tot + 2) + 4 * rows_tot * width * 2      # n_in = 1 (x), n_out = 1 (T_1)
+        return ops, xs, alg, rows_tot, nnz_tot
+
+    F_hl.enable_factored_hodge1(factored)
+    ops, xs, alg_bytes, rows_tot, nnz_tot = build(reps)
+    ms = _time_launch(lambda: F_hl.poly_basis_fwd(N.HL_LAGUERRE, 2, ops, xs, width), iters)
     ach = alg_bytes / (ms * 1e-3) / 1e9
-    out = {"bound": "hbm", "kernel": "polynomial SpMM, fused L0+L1 launch (poly_spmm_staged_kernel / poly_spmm_kernel, chosen per operator)",
+    kernel = ("factored edge Laplacian: hodge1_node_kernel + hodge1_edge_kernel<LAGUERRE_FIRST> (the launches of the timed step)"
+              if factored else "polynomial SpMM, fused L0+L1 launch (poly_spmm_staged_kernel / poly_spmm_kernel, chosen per operator)")
+    out = {"bound": "hbm", "kernel": kernel,
            "achieved": ach, "peak": pk["hbm_gbs"], "peak_kind": f"{kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
            "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
            "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": ms * 1e3,
-           "workload": f"{workload}-shaped bench batch x{reps} block-diagonal, rows {rows_tot}, nnz {nnz_tot}, F={width}; "
+           "workload": f"{workload}-shaped bench batch x{reps} block-diagonal, rows {rows_tot}, nnz(CSR) {nnz_tot}, F={width}; "
                        "inputs+outputs > L2"}
-    if workload.startswith("zinc"):
-        out["traffic"] = ncu_traffic_bytes()
-        out["traffic_source"] = "profiles/r1_spmm_v3_staged_full.txt (ncu --set full of tools/spmm_probe.py, same operator stack)"
+    del ops, xs
+    ops1, xs1, alg1, rows1, _ = build(1)
+    ms1 = _time_launch(lambda: F_hl.poly_basis_fwd(N.HL_LAGUERRE, 2, ops1, xs1, width), iters)
+    out["in_step"] = {"achieved": alg1 / (ms1 * 1e-3) / 1e9, "unit": "GB/s", "us_per_launch": ms1 * 1e3,
+                      "algorithmic_bytes_per_launch": alg1, "rows": rows1,
+                      "note": "the same launch on the bench batch itself, back to back: operator and features are L2-resident, so this "
+                              "is an L2 / launch-latency figure, not an HBM one"}
+    t = ncu_traffic(workload, factored)
+    if t is not None:
+        out["traffic"], out["traffic_source"] = t
     return out
+
+
+def ncu_traffic(workload, factored):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the committed `ncu --set full`
+    capture of this round (the same operator stack; ncu cannot run inside the bench process)."""
+    name = {("zinc", False): "r2_spmm_zinc_full.txt", ("zinc_default", False): "r2_spmm_zinc_full.txt"}.get((workload, factored))
+    if name is None:
+        return None
+    try:
+        tot = 0.0
+        for ln in open(os.path.join(ROOT, "profiles", name)):
+            if ln.startswith("dram__bytes_read.sum") or ln.startswith("dram__bytes_write.sum"):
+                val, unit = ln.split("=")[1].split()[:2]
+                tot += float(val) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
+        return (tot, f"profiles/{name} (ncu --set full of tools/spmm_probe.py, same operator stack)") if tot else None
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -222,7 +259,7 @@ def run_ours(args, world, rank, local):
     from hlhgat_b200.parallel import FlatGradBucket, broadcast_parameters
     from hlhgat_b200.synthetic import batch_to
     from hlhgat_b200.workloads import WORKLOADS
-    from hlhgat_b200.training import Capacity, pad_batch, pad_levels, padded_nbytes, GraphedTrainStep
+    from hlhgat_b200.training import Capacity, pad_batch, pad_levels, padded_nbytes, GraphedTrainStep, BatchPrefetcher
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
@@ -290,11 +327,31 @@ def run_ours(args, world, rank, local):
         stepper.batch.load(resident[i % args.pool])
         stepper.step()
 
+    prefetch = BatchPrefetcher(stepper.batch, host[0], dev)
+    loss_slots = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_events = [torch.cuda.Event(), torch.cuda.Event()]
+    state = {"primed": False, "losses": []}
+
     def step_e2e(i):                                     # host buffers in, loss out, every step
-        stepper.batch.load(host[i % args.pool], non_blocking=True)
+        # Every step's batch comes from pinned host memory; its copy is issued one step ahead on a copy stream, so it
+        # overlaps the previous step's kernels (the first step of a run pays for its own copy).  Every step's loss is
+        # read back to the host; the host consumes it one step later, so the device never idles on the read.
+        if not state["primed"]:
+            prefetch.prefetch(host[i % args.pool], i % 2)
+            state["primed"] = True
+        prefetch.swap_in(i % 2)
+        prefetch.prefetch(host[(i + 1) % args.pool], (i + 1) % 2)
         loss = stepper.step()
-        loss_host.copy_(loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        loss_slots[i % 2].copy_(loss, non_blocking=True)
+        loss_events[i % 2].record()
+        if i > 0:
+            loss_events[(i - 1) % 2].synchronize()
+            state["losses"].append(float(loss_slots[(i - 1) % 2]))
+
+    def drain_e2e(steps):
+        loss_events[(steps - 1) % 2].synchronize()
+        state["losses"].append(float(loss_slots[(steps - 1) % 2]))
+        loss_host.copy_(loss_slots[(steps - 1) % 2])
 
     for i in range(args.warmup):
         step_resident(i)
@@ -303,7 +360,17 @@ def run_ours(args, world, rank, local):
     clocks = sampler.stop() if sampler else None
     for i in range(args.warmup):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
+    drain_e2e(args.warmup)
+    state["primed"] = False
+    prefetch.stream.synchronize()
+    state["losses"].clear()
+
+    def e2e_run(i):
+        step_e2e(i)
+        if i == args.steps - 1:
+            drain_e2e(args.steps)                        # the last loss is on the host before the closing timestamp
+    ms_e2e = timed(e2e_run, args.steps)
+    assert len(state["losses"]) == args.steps
     launches = stepper.launches_per_step * args.steps
     final_loss = float(loss_host)
 
@@ -333,12 +400,15 @@ def run_ours(args, world, rank, local):
                        "gemm": "dense Theta/MLP transforms + data/weight gradients: hand-written tcgen05 3xTF32 kernels (fp32-accurate); "
                                "cuBLAS fp32 only for shapes with N % 16 != 0 or unaligned rows (first-layer inputs)"},
             "e2e": {"value": e2e, "unit": "graphs/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "pipeline": "H2D of batch i+1 on a copy stream during step i (two pinned->device staging slots, D2D into the "
+                                "graph's static buffers); the loss of every step is copied to pinned host memory and read by the "
+                                "host one step later"},
             "gpu_launches": int(launches), "gpu_launches_note": "libhlhgat kernels inside the replayed graph x steps (cuBLAS/ATen launches not counted)",
             "final_loss": final_loss, "clocks": clocks}
     try:
         b0 = raw[0][0] if wl.levels > 1 else raw[0]
-        line["roofline"] = spmm_roofline(dev, batch_to(b0, dev), args.workload)
+        line["roofline"] = spmm_roofline(dev, batch_to(b0, dev), args.workload, factored)
     except Exception as exc:  # pragma: no cover
         line["roofline"] = {"error": repr(exc)}
     try:
@@ -348,8 +418,9 @@ def run_ours(args, world, rank, local):
     if world == 1 and not args.no_cpu_baseline:
         gps, ms_cpu, cores = cpu_reference_throughput(wl, 3, 1, wl.cpu_sample)
         line["cpu_baseline"] = {"value": gps, "unit": "graphs/s", "cores": cores, "kind": "port",
-                                "sample": f"3 training steps (1 warm-up) on {wl.cpu_sample}-graph batches of the same shape, same model, "
-                                          f"{cores} torch threads; pure-torch restatement of the reference, not PyG"}
+                                "sample": f"3 training steps (1 warm-up) on {wl.cpu_sample}-graph batches "
+                                          + ("(the workload's full batch size)" if wl.cpu_sample == wl.batch else f"(bounded sample of the {wl.batch}-graph batch)")
+                                          + f" of the same shape, same model, {cores} torch threads; pure-torch restatement of the reference, not PyG"}
     print(json.dumps(line), file=_OUT, flush=True)
 
 

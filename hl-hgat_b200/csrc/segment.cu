@@ -2,6 +2,8 @@
 // cluster pooling and the per-graph readout (hl_segment_reduce, hl_endpoint_gather, hl_owner_gather,
 // hl_att_gate_fwd/bwd).  All HBM-bound; no atomics anywhere: each output row is owned by one lane
 // group that walks its CSR bucket in ascending order, so results are deterministic run to run.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hl {
@@ -102,6 +104,111 @@ segment_reduce_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restr
     }
     st_pack<V>(dst + (int64_t)row * ld_dst + col0 + ch * G * V, o);
   }
+}
+
+// The same reduction for SHORT buckets (the |B1| transfers: ~2 incident edges per node on molecular graphs, a handful on
+// kNN graphs).  With one lane group per row the kernel is a chain of three dependent global loads (rowptr -> colidx ->
+// source rows) per 2-3 gathered rows: latency-bound at ~30 % of the HBM roofline.  Here a lane group owns RB consecutive
+// rows: ONE coalesced read fetches their RB + 1 row pointers (and per-row scales), ONE read the member indices of all RB
+// buckets, and the source rows of up to four members are in flight together, whichever bucket they belong to.  Members
+// are still added in ascending bucket order into one running accumulator that is flushed at every bucket boundary, so
+// every output row sees exactly the additions of the per-row kernel, in the same order: bit-identical.
+template <int V, int CH, int RB>
+__global__ void __launch_bounds__(kSegThreads)
+segment_reduce_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int32_t nrows,
+                           const float* __restrict__ src, int64_t ld_src, const float* __restrict__ src_scale,
+                           float* __restrict__ dst, int64_t ld_dst, int32_t width, int32_t G, int post,
+                           const float* __restrict__ row_scale, float cscale) {
+  const int groups_per_block = kSegThreads / G;
+  const int gl = threadIdx.x & (G - 1);
+  const int r0 = (blockIdx.x * groups_per_block + (int)(threadIdx.x / G)) * RB;
+  if (r0 >= nrows) return;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(unsigned)(G - 1)));
+  const int col0 = blockIdx.y * (G * V * CH) + gl * V;
+  bool act[CH];
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch) act[ch] = (col0 + ch * G * V) < width;
+  const int nr = min(RB, nrows - r0);                                  // rows this group really owns
+  // lane k <= RB holds rowptr[r0 + k] (clamped) and, for k < RB, the per-row scale
+  const int myptr = __ldg(rowptr + min(r0 + min(gl, RB), nrows));
+  float myscale = 1.f;
+  if (post == HL_POST_RCP_ROW && gl < nr) myscale = __ldg(row_scale + r0 + gl);
+  const int first = __shfl_sync(gmask, myptr, 0, G), last = __shfl_sync(gmask, myptr, nr, G);
+
+  Pack<V> acc[CH];
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[ch].v[i] = 0.f;
+  int k = 0;                                                           // bucket being accumulated
+  int kstart = first, kend = __shfl_sync(gmask, myptr, 1, G);
+
+  auto flush = [&]() {                                                 // write row r0 + k, reset the accumulator, advance
+    float mul = 1.f, div = 1.f;
+    if (post == HL_POST_CONST) mul = cscale;
+    else if (post == HL_POST_RCP_ROW) mul = __fdiv_rn(1.f, __shfl_sync(gmask, myscale, k, G));
+    else if (post == HL_POST_MEAN) div = (float)max(kend - kstart, 1);
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+      if (act[ch]) {
+        Pack<V> o;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float t = acc[ch].v[i];
+          if (post == HL_POST_MEAN) t = __fdiv_rn(t, div);
+          else if (post != HL_POST_NONE) t = __fmul_rn(mul, t);
+          o.v[i] = t;
+          acc[ch].v[i] = 0.f;
+        }
+        st_pack<V>(dst + (int64_t)(r0 + k) * ld_dst + col0 + ch * G * V, o);
+      }
+    }
+    ++k;
+    kstart = kend;
+    kend = __shfl_sync(gmask, myptr, min(k + 1, RB), G);
+  };
+
+  for (int base = first; base < last; base += G) {
+    const int p = base + gl;
+    int m = 0;
+    float s = 1.f;
+    if (p < last) {
+      m = colidx ? __ldg(colidx + p) : p;
+      if (src_scale) s = __ldg(src_scale + m);
+    }
+    const int cnt = min(G, last - base);
+    for (int j = 0; j < cnt; j += 4) {
+      int mj[4];
+      float sj[4];
+      Pack<V> x[4][CH];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        mj[u] = __shfl_sync(gmask, m, min(j + u, G - 1), G);
+        sj[u] = __shfl_sync(gmask, s, min(j + u, G - 1), G);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j + u < cnt)
+#pragma unroll
+          for (int ch = 0; ch < CH; ++ch)
+            if (act[ch]) x[u][ch] = ld_pack<V>(src + (int64_t)mj[u] * ld_src + col0 + ch * G * V);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j + u >= cnt) break;
+        while (base + j + u >= kend) flush();                        // bucket boundary (also skips empty buckets)
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch)
+          if (act[ch])
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+              const float t = src_scale ? __fmul_rn(x[u][ch].v[i], sj[u]) : x[u][ch].v[i];
+              acc[ch].v[i] = __fadd_rn(acc[ch].v[i], t);
+            }
+      }
+    }
+  }
+  while (k < nr) flush();                                              // the last bucket and any empty ones after it
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -326,6 +433,24 @@ extern "C" int hl_segment_reduce(const int32_t* rowptr, const int32_t* colidx, i
   const int CH = chunks > G ? 2 : 1;
   const int tile_w = G * V * CH;
   dim3 grid((nrows + kSegThreads / G - 1) / (kSegThreads / G), (width + tile_w - 1) / tile_w);
+  // row-batched variant (8 rows per lane group; HL_SEG_ROWS=4: 4 rows) whenever a group has the lanes to hold the row
+  // pointers; HL_SEG_ROWS=0 selects the per-row kernel for A/B runs.  Measured on the x16 ZINC incidence stack (B200):
+  // s2t at F=64 1.87 -> 2.94 TB/s, at F=256 1.97 -> 3.80 TB/s; adjoint of t2s 1.96 -> 3.28 / 2.02 -> 3.98 TB/s
+  static int use_rows = -1;
+  if (use_rows < 0) { const char* e = getenv("HL_SEG_ROWS"); use_rows = e ? atoi(e) : 8; }
+  if (use_rows && G >= 16 && V == 4 && nrows >= 4096) {
+    const int RB = use_rows >= 8 ? 8 : 4;
+    const int groups = (nrows + RB - 1) / RB;
+    dim3 grid_rb((groups + kSegThreads / G - 1) / (kSegThreads / G), (width + tile_w - 1) / tile_w);
+#define HL_SEGR_CASE(CC, RR)                                                                                   \
+    segment_reduce_rows_kernel<4, CC, RR><<<grid_rb, kSegThreads, 0, as_stream(stream)>>>(                        \
+        rowptr, colidx, nrows, src, ld_src, src_scale, dst, ld_dst, width, G, post, row_scale, cscale)
+    if (RB == 8) { if (CH == 2) HL_SEGR_CASE(2, 8); else HL_SEGR_CASE(1, 8); }
+    else { if (CH == 2) HL_SEGR_CASE(2, 4); else HL_SEGR_CASE(1, 4); }
+#undef HL_SEGR_CASE
+    HL_LAUNCH_CHECK("segment_reduce_rows_kernel");
+    return HL_OK;
+  }
 #define HL_SEG_CASE(VV, CC)                                                                               \
   segment_reduce_kernel<VV, CC><<<grid, kSegThreads, 0, as_stream(stream)>>>(                              \
       rowptr, colidx, nrows, src, ld_src, src_scale, dst, ld_dst, width, G, post, row_scale, cscale)

@@ -117,9 +117,11 @@ class Incidence:
         self.num_nodes, self.num_edges = int(num_nodes), e
         self.tail = ei[0].to(torch.int32).contiguous()
         self.head = ei[1].to(torch.int32).contiguous()
+        # entries interleaved (tail[e], e), (head[e], e) for e = 0, 1, ...: position order inside a node's row IS ascending
+        # edge id, so the cheap position-stable bucketing gives the column order of the coalesced par.abs()
         ar = torch.arange(e, dtype=torch.int64, device=ei.device)
-        self.rowptr, self.edge, _, _ = csr_from_coo(ei.reshape(-1), torch.cat([ar, ar]), None,
-                                                    self.num_nodes, tie=N.HL_TIE_COLUMN)
+        self.rowptr, self.edge, _, _ = csr_from_coo(ei.t().reshape(-1), torch.repeat_interleave(ar, 2), None,
+                                                    self.num_nodes, tie=N.HL_TIE_POSITION)
 
     @classmethod
     def from_tables(cls, tail, head, rowptr, edge, num_nodes):

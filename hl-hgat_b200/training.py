@@ -132,16 +132,49 @@ class StaticBatch:
         return out
 
 
+class BatchPrefetcher:
+    """Host -> device copies off the compute stream: while step i runs, batch i + 1 travels from pinned host memory into
+    one of two staging `StaticBatch`es on a copy stream; `swap_in` then moves it into the buffers the captured step reads
+    with device-to-device copies (microseconds), ordered by events in both directions."""
+
+    def __init__(self, target, proto, device):
+        self.target, self.device = target, device
+        self.staging = [StaticBatch(proto, device), StaticBatch(proto, device)]
+        self.stream = torch.cuda.Stream(device=device)
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]        # H2D into slot done
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]         # slot read out by the compute stream
+        cur = torch.cuda.current_stream(device)
+        for ev in self.free:
+            ev.record(cur)
+
+    def prefetch(self, host_batch, slot):
+        self.stream.wait_event(self.free[slot])
+        with torch.cuda.stream(self.stream):
+            self.staging[slot].load(host_batch, non_blocking=True)
+            self.ready[slot].record(self.stream)
+
+    def swap_in(self, slot):
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self.ready[slot])
+        self.target.load(self.staging[slot])
+        self.free[slot].record(cur)
+
+
 class GraphedTrainStep:
     """forward + loss + backward captured once; replayed per step on the batch currently loaded in
     `self.batch`.  `optimizer` must be capturable (e.g. Adam(fused=True, capturable=True)).
     `criterion` is either a loss module applied to `(model(batch)[:num_graphs], batch.y)` (graph-level
     targets) or, with `loss_fn=True`, a callable `criterion(model, batch) -> scalar loss`."""
 
-    def __init__(self, model, criterion, optimizer, bucket, proto_batch, device, warmup=3, loss_fn=False):
+    def __init__(self, model, criterion, optimizer, bucket, proto_batch, device, warmup=3, loss_fn=False, single_graph=None):
+        """single_graph (default: env HL_STEP_GRAPH != "split"): the gradient all-reduce (NCCL, capturable) and the optimizer
+        step are captured into the SAME graph as forward + backward -- one cudaGraphLaunch per training step, no host
+        round trips between backward, all-reduce and Adam.  False: three launches (graph, eager all-reduce, graph)."""
+        import os
         self.model, self.criterion, self.optimizer, self.bucket = model, criterion, optimizer, bucket
         self.loss_fn = loss_fn
         self.device = device
+        self.single_graph = (os.environ.get("HL_STEP_GRAPH", "single") != "split") if single_graph is None else bool(single_graph)
         self.batch = StaticBatch(proto_batch, device)
         self.loss = torch.zeros((), device=device)
         self.split_plan = WeightSplitPlan() if warmup >= 2 else None     # recorded by the first warm-up step
@@ -158,12 +191,17 @@ class GraphedTrainStep:
         from . import _native as N
         before = N.lib().hl_launch_count()
         self.graph_fb = torch.cuda.CUDAGraph()
+        self.graph_opt = None
         with torch.cuda.graph(self.graph_fb):
             self._fwd_bwd()
-        self.launches_per_step = int(N.lib().hl_launch_count() - before)   # libhlhgat kernels in the graph
-        self.graph_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_opt, pool=self.graph_fb.pool()):
-            self.optimizer.step()
+            self.launches_per_step = int(N.lib().hl_launch_count() - before)   # libhlhgat kernels in the graph
+            if self.single_graph:
+                self.bucket.all_reduce_mean()
+                self.optimizer.step()
+        if not self.single_graph:
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt, pool=self.graph_fb.pool()):
+                self.optimizer.step()
         clear_caches()
 
     def _fwd_bwd(self):
@@ -188,6 +226,7 @@ class GraphedTrainStep:
 
     def step(self):
         self.graph_fb.replay()
-        self.bucket.all_reduce_mean()
-        self.graph_opt.replay()
+        if self.graph_opt is not None:
+            self.bucket.all_reduce_mean()
+            self.graph_opt.replay()
         return self.loss

@@ -74,7 +74,7 @@ WORKLOADS = {
     "zinc": SimpleNamespace(
         model="HL_HGCNN_zinc_dense_int3_pyr",
         ctor=dict(channels=[2, 2, 2], filters=[64, 128, 256], mlp_channels=[], K=2, node_dim=21, edge_dim=3, keig=7),
-        batch=1024, cpu_sample=256, make=_zinc_batch, levels=1, deg_eps=0.0, long_rows=False,
+        batch=1024, cpu_sample=1024, make=_zinc_batch, levels=1, deg_eps=0.0, long_rows=False,
         loss=_graph_level(torch.nn.L1Loss()), label="zinc_pyr_train_b1024_K2_fp32",
         metric="train graphs/sec ZINC-shaped (HL_HGCNN_zinc_dense_int3_pyr, batch 1024/GPU, K=2, fp32)"),
     # the same model with the defaults of main_zinc_HL_HGCNN_dense_int3_pyr.py:26-35 (SURVEY section 8d, config 2 "also report")
