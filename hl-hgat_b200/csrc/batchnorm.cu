@@ -12,6 +12,23 @@ constexpr int kBnRowsPerBlock = 128;
 
 static inline int bn_row_blocks(int32_t nrows) { return (nrows + kBnRowsPerBlock - 1) / kBnRowsPerBlock; }
 
+// Thread <-> element mapping shared by the four row-streaming kernels: a warp covers `cw` column chunks of V floats
+// (cw = power of two >= min(chunks, 32)) times 32 / cw consecutive rows, so narrow layers (F = 64: 16 chunks) keep all
+// 32 lanes busy instead of idling half of them; a thread always works on the SAME columns, so the per-column
+// parameters are loaded once, and its rows are walked four at a time with all loads of the four rows in flight.
+struct BnMap {
+  int cw, rpw, chunk, sub;      // lanes across columns, rows per warp step, this thread's chunk / row slot
+  __device__ __forceinline__ BnMap(int chunks_per_group, int lane) {
+    cw = 1;
+    while (cw < chunks_per_group && cw < 32) cw <<= 1;
+    rpw = 32 / cw;
+    chunk = lane & (cw - 1);
+    sub = lane / cw;
+  }
+};
+
+constexpr int kBnUnroll = 4;
+
 // partial[(blk * 2 + {0,1}) * width + col] = {sum (x - x[0,col]), sum (x - x[0,col])^2} over the block's rows (fp64)
 template <int V>
 __global__ void __launch_bounds__(kBnThreads)
@@ -20,16 +37,33 @@ bn_stats_partial_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows
   const int32_t nrows = nvalid ? min(__ldg(nvalid), nrows_cap) : nrows_cap;
   __shared__ float sh[2][kBnWarps][32 * V];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int col = blockIdx.y * (32 * V) + lane * V;
+  const int chunks = (min(width - (int)blockIdx.y * (32 * V), 32 * V) + V - 1) / V;
+  const BnMap mp(chunks, lane);
+  const int col = blockIdx.y * (32 * V) + mp.chunk * V;
   const int r0 = blockIdx.x * kBnRowsPerBlock;
   const int r1 = min(r0 + kBnRowsPerBlock, nrows);
-  const bool act = col < width;
+  const bool act = mp.chunk < chunks && col < width;
   Pack<V> shift, s1, s2;
 #pragma unroll
   for (int i = 0; i < V; ++i) shift.v[i] = s1.v[i] = s2.v[i] = 0.f;
   if (act && r0 < r1) {
     shift = ld_pack<V>(x + col);                             // common shift: row 0 of every column
-    for (int r = r0 + warp; r < r1; r += kBnWarps) {
+    const int step = kBnWarps * mp.rpw;
+    int r = r0 + warp * mp.rpw + mp.sub;
+    for (; r + (kBnUnroll - 1) * step < r1; r += kBnUnroll * step) {
+      Pack<V> v[kBnUnroll];
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) v[u] = ld_pack<V>(x + (int64_t)(r + u * step) * ld_x + col);
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u)
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float d = v[u].v[i] - shift.v[i];
+          s1.v[i] += d;
+          s2.v[i] = fmaf(d, d, s2.v[i]);
+        }
+    }
+    for (; r < r1; r += step) {
       Pack<V> v = ld_pack<V>(x + (int64_t)r * ld_x + col);
 #pragma unroll
       for (int i = 0; i < V; ++i) {
@@ -39,20 +73,28 @@ bn_stats_partial_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows
       }
     }
   }
+  // the row slots of a warp that share a column chunk (lanes chunk, chunk + cw, ...): fixed butterfly order
+  for (int o = mp.cw; o < 32; o <<= 1)
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    sh[0][warp][lane * V + i] = s1.v[i];
-    sh[1][warp][lane * V + i] = s2.v[i];
-  }
+    for (int i = 0; i < V; ++i) {
+      s1.v[i] += __shfl_xor_sync(0xffffffffu, s1.v[i], o);
+      s2.v[i] += __shfl_xor_sync(0xffffffffu, s2.v[i], o);
+    }
+  if (mp.sub == 0)
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      sh[0][warp][mp.chunk * V + i] = s1.v[i];
+      sh[1][warp][mp.chunk * V + i] = s2.v[i];
+    }
   __syncthreads();
-  if (warp == 0 && act) {
+  if (warp == 0 && mp.sub == 0 && act) {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       double a = 0.0, b = 0.0;
 #pragma unroll
       for (int w = 0; w < kBnWarps; ++w) {
-        a += (double)sh[0][w][lane * V + i];
-        b += (double)sh[1][w][lane * V + i];
+        a += (double)sh[0][w][mp.chunk * V + i];
+        b += (double)sh[1][w][mp.chunk * V + i];
       }
       partial[((int64_t)blockIdx.x * 2 + 0) * width + col + i] = a;
       partial[((int64_t)blockIdx.x * 2 + 1) * width + col + i] = b;
@@ -113,35 +155,47 @@ __global__ void bn_stats_final_kernel(const double* __restrict__ partial, int nb
   }
 }
 
+// y = act(gamma (x - mean) rstd + beta): grid (row blocks of 128, column groups of 32 V), the mapping of BnMap
 template <int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kBnThreads)
 bn_apply_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows, const int32_t* __restrict__ nvalid, int32_t width,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
                 float eps, float slope, float* __restrict__ y, int64_t ld_y) {
-  const int chunks = width / V;
-  const int64_t total = (int64_t)nrows * chunks;
   const int32_t nv = nvalid ? min(__ldg(nvalid), nrows) : nrows;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(idx / chunks);
-    const int col = (int)(idx - (int64_t)r * chunks) * V;
-    Pack<V> o;
-    if (r < nv) {
-      Pack<V> v = ld_pack<V>(x + (int64_t)r * ld_x + col);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunks = (min(width - (int)blockIdx.y * (32 * V), 32 * V) + V - 1) / V;
+  const BnMap mp(chunks, lane);
+  const int col = blockIdx.y * (32 * V) + mp.chunk * V;
+  if (mp.chunk >= chunks || col >= width) return;
+  const int r0 = blockIdx.x * kBnRowsPerBlock, r1 = min(r0 + kBnRowsPerBlock, nrows);
+  float mean[V], rstd[V], g[V], b[V];                         // this thread's columns: loaded once
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    mean[i] = __ldg(stats + col + i);
+    rstd[i] = rsqrtf(__ldg(stats + width + col + i) + eps);
+    g[i] = gamma ? __ldg(gamma + col + i) : 1.f;
+    b[i] = beta ? __ldg(beta + col + i) : 0.f;
+  }
+  const int step = kBnWarps * mp.rpw;
+  for (int r = r0 + warp * mp.rpw + mp.sub; r < r1; r += kBnUnroll * step) {
+    Pack<V> v[kBnUnroll];
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const int rr = r + u * step;
+      if (rr < r1 && rr < nv) v[u] = ld_pack<V>(x + (int64_t)rr * ld_x + col);
+    }
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const int rr = r + u * step;
+      if (rr >= r1) break;
+      Pack<V> o;
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        const float mean = __ldg(stats + col + i);
-        const float rstd = rsqrtf(__ldg(stats + width + col + i) + eps);
-        const float g = gamma ? __ldg(gamma + col + i) : 1.f;
-        const float b = beta ? __ldg(beta + col + i) : 0.f;
-        float t = (v.v[i] - mean) * rstd * g + b;
-        o.v[i] = t > 0.f ? t : t * slope;
+        const float t = rr < nv ? (v[u].v[i] - mean[i]) * rstd[i] * g[i] + b[i] : 0.f;
+        o.v[i] = t > 0.f ? t : t * slope;                      // ghost (padding) rows stay exactly zero
       }
-    } else {                                                 // ghost (padding) rows stay exactly zero
-#pragma unroll
-      for (int i = 0; i < V; ++i) o.v[i] = 0.f;
+      st_pack<V>(y + (int64_t)rr * ld_y + col, o);
     }
-    st_pack<V>(y + (int64_t)r * ld_y + col, o);
   }
 }
 
@@ -154,10 +208,12 @@ bn_bwd_partial_kernel(const float* __restrict__ x, int64_t ld_x, const float* __
   __shared__ float sh[2][kBnWarps][32 * V];
   const int32_t nrows = nvalid ? min(__ldg(nvalid), nrows_cap) : nrows_cap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int col = blockIdx.y * (32 * V) + lane * V;
+  const int chunks = (min(width - (int)blockIdx.y * (32 * V), 32 * V) + V - 1) / V;
+  const BnMap mp(chunks, lane);
+  const int col = blockIdx.y * (32 * V) + mp.chunk * V;
   const int r0 = blockIdx.x * kBnRowsPerBlock;
   const int r1 = min(r0 + kBnRowsPerBlock, nrows);
-  const bool act = col < width;
+  const bool act = mp.chunk < chunks && col < width;
   Pack<V> s1, s2;
 #pragma unroll
   for (int i = 0; i < V; ++i) s1.v[i] = s2.v[i] = 0.f;
@@ -168,32 +224,51 @@ bn_bwd_partial_kernel(const float* __restrict__ x, int64_t ld_x, const float* __
       mean[i] = __ldg(stats + col + i);
       rstd[i] = rsqrtf(__ldg(stats + width + col + i) + eps);
     }
-    for (int r = r0 + warp; r < r1; r += kBnWarps) {
-      Pack<V> xv = ld_pack<V>(x + (int64_t)r * ld_x + col);
-      Pack<V> yv = ld_pack<V>(y + (int64_t)r * ld_y + col);
-      Pack<V> gv = ld_pack<V>(dy + (int64_t)r * ld_dy + col);
+    const int step = kBnWarps * mp.rpw;
+    for (int r = r0 + warp * mp.rpw + mp.sub; r < r1; r += kBnUnroll * step) {
+      Pack<V> xv[kBnUnroll], yv[kBnUnroll], gv[kBnUnroll];
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float dz = yv.v[i] > 0.f ? gv.v[i] : gv.v[i] * slope;
-        s1.v[i] += dz;
-        s2.v[i] = fmaf(dz, (xv.v[i] - mean[i]) * rstd[i], s2.v[i]);
+      for (int u = 0; u < kBnUnroll; ++u) {
+        const int rr = r + u * step;
+        if (rr < r1) {
+          xv[u] = ld_pack<V>(x + (int64_t)rr * ld_x + col);
+          yv[u] = ld_pack<V>(y + (int64_t)rr * ld_y + col);
+          gv[u] = ld_pack<V>(dy + (int64_t)rr * ld_dy + col);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        if (r + u * step >= r1) break;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float dz = yv[u].v[i] > 0.f ? gv[u].v[i] : gv[u].v[i] * slope;
+          s1.v[i] += dz;
+          s2.v[i] = fmaf(dz, (xv[u].v[i] - mean[i]) * rstd[i], s2.v[i]);
+        }
       }
     }
   }
+  for (int o = mp.cw; o < 32; o <<= 1)
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    sh[0][warp][lane * V + i] = s1.v[i];
-    sh[1][warp][lane * V + i] = s2.v[i];
-  }
+    for (int i = 0; i < V; ++i) {
+      s1.v[i] += __shfl_xor_sync(0xffffffffu, s1.v[i], o);
+      s2.v[i] += __shfl_xor_sync(0xffffffffu, s2.v[i], o);
+    }
+  if (mp.sub == 0)
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      sh[0][warp][mp.chunk * V + i] = s1.v[i];
+      sh[1][warp][mp.chunk * V + i] = s2.v[i];
+    }
   __syncthreads();
-  if (warp == 0 && act) {
+  if (warp == 0 && mp.sub == 0 && act) {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       double a = 0.0, b = 0.0;
 #pragma unroll
       for (int w = 0; w < kBnWarps; ++w) {
-        a += (double)sh[0][w][lane * V + i];
-        b += (double)sh[1][w][lane * V + i];
+        a += (double)sh[0][w][mp.chunk * V + i];
+        b += (double)sh[1][w][mp.chunk * V + i];
       }
       partial[((int64_t)blockIdx.x * 2 + 0) * width + col + i] = a;
       partial[((int64_t)blockIdx.x * 2 + 1) * width + col + i] = b;
@@ -216,45 +291,58 @@ __global__ void bn_bwd_final_kernel(const double* __restrict__ partial, int nblk
 }
 
 template <int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kBnThreads)
 bn_bwd_apply_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ y, int64_t ld_y,
                     const float* __restrict__ dy, int64_t ld_dy, int32_t nrows, const int32_t* __restrict__ nvalid, int32_t width,
                     const float* __restrict__ gamma, const float* __restrict__ stats, const float* __restrict__ sums,
                     float eps, float slope, float* __restrict__ dx, int64_t ld_dx, const float* __restrict__ inv_count) {
-  const int chunks = width / V;
-  const int64_t total = (int64_t)nrows * chunks;
   const int32_t nv = nvalid ? min(__ldg(nvalid), nrows) : nrows;
   const float inv_n = inv_count ? __ldg(inv_count) : 1.f / (float)max(nv, 1);   // inv_count: 1 / rows over ALL ranks (SyncBN)
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(idx / chunks);
-    const int col = (int)(idx - (int64_t)r * chunks) * V;
-    Pack<V> o;
-    if (r < nv) {
-      Pack<V> xv = ld_pack<V>(x + (int64_t)r * ld_x + col);
-      Pack<V> yv = ld_pack<V>(y + (int64_t)r * ld_y + col);
-      Pack<V> gv = ld_pack<V>(dy + (int64_t)r * ld_dy + col);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunks = (min(width - (int)blockIdx.y * (32 * V), 32 * V) + V - 1) / V;
+  const BnMap mp(chunks, lane);
+  const int col = blockIdx.y * (32 * V) + mp.chunk * V;
+  if (mp.chunk >= chunks || col >= width) return;
+  const int r0 = blockIdx.x * kBnRowsPerBlock, r1 = min(r0 + kBnRowsPerBlock, nrows);
+  float mean[V], rstd[V], g[V], m1[V], m2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    mean[i] = __ldg(stats + col + i);
+    rstd[i] = rsqrtf(__ldg(stats + width + col + i) + eps);
+    g[i] = gamma ? __ldg(gamma + col + i) : 1.f;
+    m1[i] = __ldg(sums + col + i) * inv_n;
+    m2[i] = __ldg(sums + width + col + i) * inv_n;
+  }
+  const int step = kBnWarps * mp.rpw;
+  for (int r = r0 + warp * mp.rpw + mp.sub; r < r1; r += kBnUnroll * step) {
+    Pack<V> xv[kBnUnroll], yv[kBnUnroll], gv[kBnUnroll];
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const int rr = r + u * step;
+      if (rr < r1 && rr < nv) {
+        xv[u] = ld_pack<V>(x + (int64_t)rr * ld_x + col);
+        yv[u] = ld_pack<V>(y + (int64_t)rr * ld_y + col);
+        gv[u] = ld_pack<V>(dy + (int64_t)rr * ld_dy + col);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const int rr = r + u * step;
+      if (rr >= r1) break;
+      Pack<V> o;
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        const float mean = __ldg(stats + col + i);
-        const float rstd = rsqrtf(__ldg(stats + width + col + i) + eps);
-        const float g = gamma ? __ldg(gamma + col + i) : 1.f;
-        const float dz = yv.v[i] > 0.f ? gv.v[i] : gv.v[i] * slope;
-        const float xh = (xv.v[i] - mean) * rstd;
-        o.v[i] = g * rstd * (dz - __ldg(sums + col + i) * inv_n - xh * __ldg(sums + width + col + i) * inv_n);
+        if (rr < nv) {
+          const float dz = yv[u].v[i] > 0.f ? gv[u].v[i] : gv[u].v[i] * slope;
+          const float xh = (xv[u].v[i] - mean[i]) * rstd[i];
+          o.v[i] = g[i] * rstd[i] * (dz - m1[i] - xh * m2[i]);
+        } else {
+          o.v[i] = 0.f;
+        }
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < V; ++i) o.v[i] = 0.f;
+      st_pack<V>(dx + (int64_t)rr * ld_dx + col, o);
     }
-    st_pack<V>(dx + (int64_t)r * ld_dx + col, o);
   }
-}
-
-static int ew_grid(int64_t total) {
-  int64_t b = (total + 255) / 256;
-  const int64_t cap = 148LL * 16;
-  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
 }  // namespace hl
@@ -288,10 +376,9 @@ extern "C" int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_
                                                                     running_mean, running_mean ? running_var : nullptr, momentum,
                                                                     reinterpret_cast<long long*>(num_batches_tracked));
   HL_LAUNCH_CHECK("bn_stats_final_kernel");
-  const int g = ew_grid((int64_t)nrows * (width / V));
-  if (V == 4) bn_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
-  else if (V == 2) bn_apply_kernel<2><<<g, 256, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
-  else bn_apply_kernel<1><<<g, 256, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  if (V == 4) bn_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else if (V == 2) bn_apply_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else bn_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
   HL_LAUNCH_CHECK("bn_apply_kernel");
   return HL_OK;
 }
@@ -320,10 +407,9 @@ extern "C" int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64
   HL_LAUNCH_CHECK("bn_bwd_partial_kernel");
   bn_bwd_final_kernel<<<(width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st>>>(partial, nblk, width, sums, dgamma, dbeta, accumulate_param_grads);
   HL_LAUNCH_CHECK("bn_bwd_final_kernel");
-  const int g = ew_grid((int64_t)nrows * (width / V));
-  if (V == 4) bn_bwd_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
-  else if (V == 2) bn_bwd_apply_kernel<2><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
-  else bn_bwd_apply_kernel<1><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
+  if (V == 4) bn_bwd_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
+  else if (V == 2) bn_bwd_apply_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
+  else bn_bwd_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
   HL_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return HL_OK;
 }
@@ -360,10 +446,10 @@ extern "C" int hl_bn_apply(const float* x, int64_t ld_x, int32_t nrows, int32_t 
   cudaStream_t st = as_stream(stream);
   int V = vec_for(x, ld_x, width, 4);
   V = min(V, vec_for(y, ld_y, width, V));
-  const int g = ew_grid((int64_t)nrows * (width / V));
-  if (V == 4) bn_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
-  else if (V == 2) bn_apply_kernel<2><<<g, 256, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
-  else bn_apply_kernel<1><<<g, 256, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  dim3 grid(bn_row_blocks(nrows), (width + 32 * V - 1) / (32 * V));
+  if (V == 4) bn_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else if (V == 2) bn_apply_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else bn_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
   HL_LAUNCH_CHECK("bn_apply_kernel");
   return HL_OK;
 }
@@ -401,10 +487,10 @@ extern "C" int hl_bn_bwd_apply(const float* x, int64_t ld_x, const float* y, int
   V = min(V, vec_for(y, ld_y, width, V));
   V = min(V, vec_for(dy, ld_dy, width, V));
   V = min(V, vec_for(dx, ld_dx, width, V));
-  const int g = ew_grid((int64_t)nrows * (width / V));
-  if (V == 4) bn_bwd_apply_kernel<4><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
-  else if (V == 2) bn_bwd_apply_kernel<2><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
-  else bn_bwd_apply_kernel<1><<<g, 256, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
+  dim3 grid(bn_row_blocks(nrows), (width + 32 * V - 1) / (32 * V));
+  if (V == 4) bn_bwd_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
+  else if (V == 2) bn_bwd_apply_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
+  else bn_bwd_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
   HL_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return HL_OK;
 }
