@@ -87,7 +87,7 @@ _SIGNATURES = {
     "hl_greedy_matching": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hl_bn_workspace": (_sz, [_i32, _i32]),
     "hl_bn_act_fwd": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _vp, _i64, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _sz, _vp]),
-    "hl_bn_act_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32,
+    "hl_bn_act_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32,
                                 _vp, _i64, _vp, _vp, C.c_int, _vp, _vp, _sz, _vp]),
     "hl_bn_stats": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "hl_bn_apply": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _f32, _f32, _vp, _i64, _vp, _vp]),

@@ -203,7 +203,8 @@ bn_apply_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows, const 
 template <int V>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_partial_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ y, int64_t ld_y,
-                      const float* __restrict__ dy, int64_t ld_dy, int32_t nrows_cap, const int32_t* __restrict__ nvalid,
+                      const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ dy2, int64_t ld_dy2,
+                      int32_t nrows_cap, const int32_t* __restrict__ nvalid,
                       int32_t width, const float* __restrict__ stats, float eps, float slope, double* __restrict__ partial) {
   __shared__ float sh[2][kBnWarps][32 * V];
   const int32_t nrows = nvalid ? min(__ldg(nvalid), nrows_cap) : nrows_cap;
@@ -234,6 +235,11 @@ bn_bwd_partial_kernel(const float* __restrict__ x, int64_t ld_x, const float* __
           xv[u] = ld_pack<V>(x + (int64_t)rr * ld_x + col);
           yv[u] = ld_pack<V>(y + (int64_t)rr * ld_y + col);
           gv[u] = ld_pack<V>(dy + (int64_t)rr * ld_dy + col);
+          if (dy2) {                                             // the gradient arrives in two pieces: summed on the fly
+            const Pack<V> g2 = ld_pack<V>(dy2 + (int64_t)rr * ld_dy2 + col);
+#pragma unroll
+            for (int i = 0; i < V; ++i) gv[u].v[i] += g2.v[i];
+          }
         }
       }
 #pragma unroll
@@ -293,7 +299,8 @@ __global__ void bn_bwd_final_kernel(const double* __restrict__ partial, int nblk
 template <int V>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_apply_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ y, int64_t ld_y,
-                    const float* __restrict__ dy, int64_t ld_dy, int32_t nrows, const int32_t* __restrict__ nvalid, int32_t width,
+                    const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ dy2, int64_t ld_dy2,
+                    int32_t nrows, const int32_t* __restrict__ nvalid, int32_t width,
                     const float* __restrict__ gamma, const float* __restrict__ stats, const float* __restrict__ sums,
                     float eps, float slope, float* __restrict__ dx, int64_t ld_dx, const float* __restrict__ inv_count) {
   const int32_t nv = nvalid ? min(__ldg(nvalid), nrows) : nrows;
@@ -323,6 +330,11 @@ bn_bwd_apply_kernel(const float* __restrict__ x, int64_t ld_x, const float* __re
         xv[u] = ld_pack<V>(x + (int64_t)rr * ld_x + col);
         yv[u] = ld_pack<V>(y + (int64_t)rr * ld_y + col);
         gv[u] = ld_pack<V>(dy + (int64_t)rr * ld_dy + col);
+        if (dy2) {
+          const Pack<V> g2 = ld_pack<V>(dy2 + (int64_t)rr * ld_dy2 + col);
+#pragma unroll
+          for (int i = 0; i < V; ++i) gv[u].v[i] += g2.v[i];
+        }
       }
     }
 #pragma unroll
@@ -384,7 +396,7 @@ extern "C" int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_
 }
 
 extern "C" int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64_t ld_y,
-                             const float* dy, int64_t ld_dy, int32_t nrows, int32_t width,
+                             const float* dy, int64_t ld_dy, const float* dy2, int64_t ld_dy2, int32_t nrows, int32_t width,
                              const float* gamma, const float* stats, float eps, float slope,
                              float* dx, int64_t ld_dx, float* dgamma, float* dbeta, int accumulate_param_grads,
                              const int32_t* nvalid, void* workspace, size_t workspace_bytes, hl_stream_t stream) {
@@ -399,17 +411,18 @@ extern "C" int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64
   int V = vec_for(x, ld_x, width, 4);
   V = min(V, vec_for(y, ld_y, width, V));
   V = min(V, vec_for(dy, ld_dy, width, V));
+  V = min(V, vec_for(dy2, ld_dy2, width, V));
   V = min(V, vec_for(dx, ld_dx, width, V));
   dim3 grid(nblk, (width + 32 * V - 1) / (32 * V));
-  if (V == 4) bn_bwd_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
-  else if (V == 2) bn_bwd_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
-  else bn_bwd_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
+  if (V == 4) bn_bwd_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
+  else if (V == 2) bn_bwd_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
+  else bn_bwd_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
   HL_LAUNCH_CHECK("bn_bwd_partial_kernel");
   bn_bwd_final_kernel<<<(width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st>>>(partial, nblk, width, sums, dgamma, dbeta, accumulate_param_grads);
   HL_LAUNCH_CHECK("bn_bwd_final_kernel");
-  if (V == 4) bn_bwd_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
-  else if (V == 2) bn_bwd_apply_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
-  else bn_bwd_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
+  if (V == 4) bn_bwd_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
+  else if (V == 2) bn_bwd_apply_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
+  else bn_bwd_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
   HL_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return HL_OK;
 }
@@ -460,6 +473,8 @@ extern "C" int hl_bn_bwd_sums(const float* x, int64_t ld_x, const float* y, int6
   using namespace hl;
   if (nrows < 1 || width < 1 || !x || !y || !dy || !stats || !sums) return HL_ERR_INVALID;
   if (!workspace || workspace_bytes < hl_bn_workspace(nrows, width)) return HL_ERR_WORKSPACE;
+  const float* dy2 = nullptr;
+  const int64_t ld_dy2 = 0;
   cudaStream_t st = as_stream(stream);
   const int nblk = bn_row_blocks(nrows);
   double* partial = reinterpret_cast<double*>(workspace);
@@ -467,9 +482,9 @@ extern "C" int hl_bn_bwd_sums(const float* x, int64_t ld_x, const float* y, int6
   V = min(V, vec_for(y, ld_y, width, V));
   V = min(V, vec_for(dy, ld_dy, width, V));
   dim3 grid(nblk, (width + 32 * V - 1) / (32 * V));
-  if (V == 4) bn_bwd_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
-  else if (V == 2) bn_bwd_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
-  else bn_bwd_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, stats, eps, slope, partial);
+  if (V == 4) bn_bwd_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
+  else if (V == 2) bn_bwd_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
+  else bn_bwd_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
   HL_LAUNCH_CHECK("bn_bwd_partial_kernel");
   bn_bwd_final_kernel<<<(width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st>>>(partial, nblk, width, sums, nullptr, nullptr, 0);
   HL_LAUNCH_CHECK("bn_bwd_final_kernel");
@@ -482,15 +497,17 @@ extern "C" int hl_bn_bwd_apply(const float* x, int64_t ld_x, const float* y, int
                                const int32_t* nvalid, hl_stream_t stream) {
   using namespace hl;
   if (nrows < 1 || width < 1 || !x || !y || !dy || !dx || !stats || !sums) return HL_ERR_INVALID;
+  const float* dy2 = nullptr;
+  const int64_t ld_dy2 = 0;
   cudaStream_t st = as_stream(stream);
   int V = vec_for(x, ld_x, width, 4);
   V = min(V, vec_for(y, ld_y, width, V));
   V = min(V, vec_for(dy, ld_dy, width, V));
   V = min(V, vec_for(dx, ld_dx, width, V));
   dim3 grid(bn_row_blocks(nrows), (width + 32 * V - 1) / (32 * V));
-  if (V == 4) bn_bwd_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
-  else if (V == 2) bn_bwd_apply_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
-  else bn_bwd_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
+  if (V == 4) bn_bwd_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
+  else if (V == 2) bn_bwd_apply_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
+  else bn_bwd_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
   HL_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return HL_OK;
 }

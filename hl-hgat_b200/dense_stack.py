@@ -149,14 +149,17 @@ class DenseStack:
             _alias(gbuf, f, d).copy_(g[:, f:d])
         self.filled[(kind, side)] = max(self.filled[(kind, side)], d)
 
-    def collect(self, kind, side, c0, c1, g):
-        """Total gradient of block [c0, c1): what the stack consumers accumulated (if any) plus autograd's `g`."""
+    def collect(self, kind, side, c0, c1, g, fuse=False):
+        """Total gradient of block [c0, c1): what the stack consumers accumulated (if any) plus autograd's `g`.
+        fuse=True: returns the two pieces `(a, b)` (b may be None) for a consumer that adds them itself."""
         # `filled`: leading columns some consumer's backward has written.  A consumer whose output did not reach the loss
         # (e.g. the gate of the last stage when only the prediction is trained) never runs and leaves no gradient here;
         # the autograd engine runs every consumer that does BEFORE the producer of the block (they are its graph children)
         if self.filled[(kind, side)] < c1:
-            return g
+            return (g, None) if fuse else g
         sl = _alias(self._gbuf(kind, side), c0, c1)
+        if fuse:
+            return sl, g
         if g is not None:
             sl.add_(g)
         return sl

@@ -761,14 +761,20 @@ class Segments:
         return cls(rowptr, members, owner, nrows, idx.numel())
 
     @classmethod
-    def from_counts(cls, counts, total=None):
+    def from_counts(cls, counts, total=None, ghost_last=False):
         """Contiguous segments (sorted `batch` vector): counts[g] rows per graph.  Pass `total`
-        (= counts.sum(), known on the host) to stay free of device->host syncs (CUDA-graph capture)."""
+        (= counts.sum(), known on the host) to stay free of device->host syncs (CUDA-graph capture).
+        ghost_last: the last segment is the ghost graph of a padded fixed-capacity batch (training.pad_batch) -- hundreds
+        of all-zero rows that one lane group would walk serially; it is left EMPTY (its mean is the same zero row) and
+        its rows own nothing."""
         counts = counts.to(torch.int64)
-        ptr = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=counts.device)
-        ptr[1:] = torch.cumsum(counts, 0)
         ids = torch.arange(counts.numel(), device=counts.device, dtype=torch.int32)
         owner = torch.repeat_interleave(ids, counts, output_size=total)
+        if ghost_last:                              # device-side only (captured into the step graph)
+            counts = torch.where(ids == counts.numel() - 1, torch.zeros_like(counts), counts)
+            owner = torch.where(owner == counts.numel() - 1, torch.full_like(owner, -1), owner)
+        ptr = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=counts.device)
+        ptr[1:] = torch.cumsum(counts, 0)
         return cls(ptr, None, owner, counts.numel(), int(owner.numel()))
 
 
@@ -839,8 +845,9 @@ class _BnAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _):
-        if ctx.tap is not None:
-            dy = ctx.tap[0].collect("own", *ctx.tap[1:], dy)
+        dy2 = None
+        if ctx.tap is not None:                     # stack-accumulated gradient + autograd's piece: summed inside the kernels
+            dy, dy2 = ctx.tap[0].collect("own", *ctx.tap[1:], dy, fuse=True)
         if dy is None:
             return (None,) * 11
         if ctx.empty:
@@ -849,6 +856,9 @@ class _BnAct(torch.autograd.Function):
         L = N.lib()
         R, F = x.shape
         dy, lddy = N.row_major(dy)
+        lddy2 = 0
+        if dy2 is not None:
+            dy2, lddy2 = N.row_major(dy2)
         dx = torch.empty((R, F), dtype=torch.float32, device=x.device)
         tg, tb = _grad_target(ctx.params[0]), _grad_target(ctx.params[1])
         fused = tg is not None and tb is not None
@@ -856,7 +866,7 @@ class _BnAct(torch.autograd.Function):
         dbeta = tb if fused else torch.empty(F, dtype=torch.float32, device=x.device)
         nb = L.hl_bn_workspace(R, F)
         ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
-        N.check(L.hl_bn_act_bwd(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), dy.data_ptr(), lddy, R, F,
+        N.check(L.hl_bn_act_bwd(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), dy.data_ptr(), lddy, N.ptr(dy2), lddy2, R, F,
                                 N.ptr(gamma), stats.data_ptr(), ctx.eps, ctx.slope, dx.data_ptr(), dx.stride(0),
                                 dgamma.data_ptr(), dbeta.data_ptr(), 1 if fused else 0, N.ptr(ctx.nvalid), ws.data_ptr(), nb,
                                 N.stream_ptr()), "hl_bn_act_bwd")

@@ -72,8 +72,8 @@ class HL_HGCNN_zinc_dense_int3_pyr(nn.Module):
         # operators are bucketed once per batch; every layer below reuses the CSR tables
         op_t = operator_for(data.edge_index_t, data.edge_weight_t, n)
         op_s = operator_for(data.edge_index_s, data.edge_weight_s, e)
-        seg_t = F_hl.Segments.from_counts(torch.as_tensor(data.num_node1, device=x_t.device), total=n)
-        seg_s = F_hl.Segments.from_counts(torch.as_tensor(data.num_edge1, device=x_t.device), total=e)
+        seg_t = F_hl.Segments.from_counts(torch.as_tensor(data.num_node1, device=x_t.device), total=n, ghost_last=nv_g is not None)
+        seg_s = F_hl.Segments.from_counts(torch.as_tensor(data.num_edge1, device=x_t.device), total=e, ghost_last=nv_g is not None)
         inc = incidence_for(data.edge_index, n)
         D = getattr(data, "D", None)
         if D is None:
@@ -138,10 +138,13 @@ class _Level:
         self.nv_g = getattr(d, "n_valid_graphs", None)
         self._d, self._device = d, device
 
-    def segments(self):
+    def segments(self, readout=False):
+        """Per-graph row segments; readout=True: for the mean readout of a padded batch the ghost graph's segment is
+        left empty (Segments.from_counts)."""
         d, dev = self._d, self._device
-        return (F_hl.Segments.from_counts(torch.as_tensor(d.num_node1, device=dev), total=self.n),
-                F_hl.Segments.from_counts(torch.as_tensor(d.num_edge1, device=dev), total=self.e))
+        ghost = readout and self.nv_g is not None
+        return (F_hl.Segments.from_counts(torch.as_tensor(d.num_node1, device=dev), total=self.n, ghost_last=ghost),
+                F_hl.Segments.from_counts(torch.as_tensor(d.num_edge1, device=dev), total=self.e, ghost_last=ghost))
 
 
 def _stage(self, i, lv, stack, keep_last=True):
@@ -248,7 +251,7 @@ class _AttPool(nn.Module):
         return F_hl.Segments.from_index(pos_t, nrows=n1), F_hl.Segments.from_index(pos_s, nrows=e1)
 
     def _head(self, x_t, x_s, lv):
-        seg_n, seg_e = lv.segments()
+        seg_n, seg_e = lv.segments(readout=True)
         x = torch.cat((F_hl.segment_mean(x_s, seg_e), F_hl.segment_mean(x_t, seg_n)), -1)
         for i, _ in enumerate(self.mlp_channels):
             x = getattr(self, "mlp%d" % i)(x, lv.nv_g)

@@ -252,7 +252,8 @@ int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_t width,
                   int64_t* num_batches_tracked /* device, nullable: incremented by one in the same launch */,
                   void* workspace, size_t workspace_bytes, hl_stream_t stream);
 int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64_t ld_y,
-                  const float* dy, int64_t ld_dy, int32_t nrows, int32_t width,
+                  const float* dy, int64_t ld_dy, const float* dy2 /* nullable: a second gradient piece, added on the fly */, int64_t ld_dy2,
+                  int32_t nrows, int32_t width,
                   const float* gamma, const float* stats, float eps, float slope,
                   float* dx, int64_t ld_dx, float* dgamma, float* dbeta,
                   int accumulate_param_grads /* dgamma / dbeta: 0 = overwrite, 1 = += (fused gradient accumulation) */,
