@@ -130,6 +130,8 @@ struct GemmParams {
   int32_t tmem_a_col;       // TS variant: first TMEM column of the A_hi | A_lo slots (64 columns per ring stage)
   int32_t conv_groups;      // converter groups taking alternate ring stages: 1 (192 threads) or 2 (320 threads)
   float* colsum_ws;         // wgrad TS: per-split column sums of G, [splits][M] (the bias gradient falls out of the A pass)
+  int32_t num_tiles, tiles_n;   // persistent kernel: output tiles in total / along N
+  int32_t acc_stride;           // persistent kernel: TMEM columns between the two accumulators
 };
 
 // MODE 0: C = A[M,K] B[N,K]^T, both K-major, B pre-split (map_b = hi, map_b2 = lo).
@@ -452,6 +454,233 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent forward / data-gradient kernel (MODE 0 with the A operand in tensor memory).
+//
+// ncu on the one-tile-per-CTA kernel above (profiles/r2_gemm_k256_one_tile_kernel_full.txt): at K = 256 the tensor pipe is active 38 % of
+// the time and the SMs sit idle for 29 % of the launch -- L2 and DRAM are far from their limits (13 % / 10 %), the time
+// goes into what every CTA pays around its 8 k-blocks: barrier init, TMEM allocation, descriptor fetch, pipeline fill,
+// and an epilogue that the converter warps run AFTER the main loop.  Here one CTA per SM walks its share of the output
+// tiles: the ring (TMA -> A split into tensor memory -> tcgen05.mma) never drains between tiles, the accumulator is
+// DOUBLE-BUFFERED in tensor memory (2 x bn columns + 4 x 64 columns of A slots = all 512), and four dedicated epilogue
+// warps drain accumulator b (TMEM -> registers -> padded staging tile -> full 128-byte row segments) while the MMA warp
+// already fills accumulator 1 - b with the next tile.
+//   warp 0      TMA producer          warp 1      tcgen05.mma issue (one lane)
+//   warps 2-5   A converters          warps 6-9   epilogue
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kPsThreads = 320;
+constexpr int kPsPitch = 36;                                  // floats per staged epilogue row (144 B: conflict-free float4)
+
+__global__ void __launch_bounds__(kPsThreads, 1)
+gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+                              const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_a2,
+                              const GemmParams P) {
+  extern __shared__ __align__(1024) unsigned char gm_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bn = P.bn, stages = P.stages;
+  const uint32_t a_bytes = kGmBM * kGmBK * 4, b_bytes = (uint32_t)bn * kGmBK * 4;
+  const uint32_t stage_bytes = a_bytes + 2 * b_bytes;
+  unsigned char* base = gm_smem;
+  float* staging = reinterpret_cast<float*>(base + (size_t)stages * stage_bytes);          // [4 warps][32 rows][kPsPitch]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(staging) + 4 * 32 * kPsPitch * 4);
+  uint64_t* full_bar = bars;                 // [stages]  TMA bytes landed
+  uint64_t* conv_bar = bars + stages;        // [stages]  A split written to tensor memory
+  uint64_t* empty_bar = bars + 2 * stages;   // [stages]  MMAs of the stage retired
+  uint64_t* acc_full = bars + 3 * stages;    // [2]       accumulator b complete
+  uint64_t* acc_empty = acc_full + 2;        // [2]       accumulator b drained by the epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int num_kb = (P.K + kGmBK - 1) / kGmBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      gm_mbar_init(&full_bar[s], 1);
+      gm_mbar_init(&conv_bar[s], kGmConvThreads);
+      gm_mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      gm_mbar_init(&acc_full[b], 1);
+      gm_mbar_init(&acc_empty[b], 4);                               // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gm_smem_u32(tmem_slot)),
+                 "r"((uint32_t)P.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------ TMA producer ------------------------------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / P.tiles_n) * kGmBM, n0 = (tile % P.tiles_n) * bn;
+        for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == stages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
+          gm_mbar_wait(&empty_bar[s], ph ^ 1u);
+          unsigned char* st = base + (size_t)s * stage_bytes;
+          gm_mbar_arrive_expect_tx(&full_bar[s], a_bytes + 2 * b_bytes);
+          if (kb < P.kb_first) gm_tma_load_2d(st, &map_a, &full_bar[s], kb * kGmBK, m0);
+          else gm_tma_load_2d(st, &map_a2, &full_bar[s], (kb - P.kb_first) * kGmBK, m0);
+          gm_tma_load_2d(st + a_bytes, &map_bhi, &full_bar[s], kb * kGmBK, n0);
+          gm_tma_load_2d(st + a_bytes + b_bytes, &map_blo, &full_bar[s], kb * kGmBK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------ MMA issuer ------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kGmBM >> 4) << 24);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        gm_mbar_wait(&acc_empty[b], (uint32_t)((it >> 1) & 1) ^ 1u);       // the epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(b * P.acc_stride);
+        for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == stages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
+          gm_mbar_wait(&conv_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = gm_smem_u32(base + (size_t)s * stage_bytes);
+          const uint32_t b_hi = st + a_bytes, b_lo = st + a_bytes + b_bytes;
+          const uint32_t ta_hi = tmem_base + (uint32_t)P.tmem_a_col + (uint32_t)s * 64u, ta_lo = ta_hi + 32u;
+#pragma unroll
+          for (int k = 0; k < kGmBK / 8; ++k) {
+            const uint64_t dbh = gm_desc_kmajor_sw128(b_hi + (uint32_t)k * 32u);
+            const uint64_t dbl = gm_desc_kmajor_sw128(b_lo + (uint32_t)k * 32u);
+            gm_mma_tf32_ts(d_tmem, ta_lo + 8u * k, dbh, idesc, (kb | k) ? 1u : 0u);   // small terms first
+            gm_mma_tf32_ts(d_tmem, ta_hi + 8u * k, dbl, idesc, 1u);
+            gm_mma_tf32_ts(d_tmem, ta_hi + 8u * k, dbh, idesc, 1u);
+          }
+          gm_commit(&empty_bar[s]);
+        }
+        gm_commit(&acc_full[b]);
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------ A converters ------------------------------------
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == stages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
+        gm_mbar_wait(&full_bar[s], ph);
+        uint32_t hi[32], lo[32];
+        const unsigned char* arow = base + (size_t)s * stage_bytes + (size_t)r * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 x = *reinterpret_cast<const float4*>(arow + ((c ^ (r & 7)) << 4));
+          const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint32_t h = __float_as_uint(xs[t]) & 0xffffe000u;
+            hi[4 * c + t] = h;
+            lo[4 * c + t] = __float_as_uint(xs[t] - __uint_as_float(h));
+          }
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)P.tmem_a_col + (uint32_t)s * 64u;
+        gm_tmem_st_x32(taddr, hi);
+        gm_tmem_st_x32(taddr + 32u, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        gm_mbar_arrive(&conv_bar[s]);
+      }
+    }
+  } else {
+    // ------------------------------------ epilogue ------------------------------------
+    const int quad = warp & 3;                                       // TMEM lane quadrant this warp may read
+    float* stage_tile = staging + (size_t)(warp - 6) * 32 * kPsPitch;
+    const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
+    const bool vec_ok = (P.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      const int m0 = (tile / P.tiles_n) * kGmBM, n0 = (tile % P.tiles_n) * bn;
+      gm_mbar_wait(&acc_full[b], (uint32_t)((it >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c = 0; c < bn; c += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * P.acc_stride + c);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+        if (vec_ok) {
+          const int col = n0 + c + sub_col;
+          const bool col_ok = col + 3 < P.N && c + sub_col < bn;
+          float4 old[8];
+          if (P.accumulate) {
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8) {
+              const int rr = m0 + quad * 32 + i8 * 4 + sub_row;
+              old[i8] = (col_ok && rr < P.M) ? *reinterpret_cast<const float4*>(P.C + (int64_t)rr * P.ldc + col)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (P.bias && col_ok) {
+            if ((reinterpret_cast<uintptr_t>(P.bias) & 15) == 0) bv = __ldg(reinterpret_cast<const float4*>(P.bias + col));
+            else bv = make_float4(__ldg(P.bias + col), __ldg(P.bias + col + 1), __ldg(P.bias + col + 2), __ldg(P.bias + col + 3));
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float* mine = stage_tile + lane * kPsPitch;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(mine + j) =
+                make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          __syncwarp();
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int lr = i8 * 4 + sub_row;
+            const int rr = m0 + quad * 32 + lr;
+            float4 v = *reinterpret_cast<const float4*>(stage_tile + lr * kPsPitch + sub_col);
+            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            if (P.accumulate) { v.x += old[i8].x; v.y += old[i8].y; v.z += old[i8].z; v.w += old[i8].w; }
+            if (col_ok && rr < P.M) *reinterpret_cast<float4*>(P.C + (int64_t)rr * P.ldc + col) = v;
+          }
+          __syncwarp();
+          continue;
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int row = m0 + quad * 32 + lane;
+        if (row < P.M) {
+          float* crow = P.C + (int64_t)row * P.ldc + n0 + c;
+          for (int j = 0; j < 32; ++j) {
+            const int col = n0 + c + j;
+            if (col >= P.N || c + j >= bn) break;
+            float v = __uint_as_float(r[j]);
+            if (P.bias) v += __ldg(P.bias + col);
+            crow[j] = P.accumulate ? crow[j] + v : v;
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) gm_mbar_arrive(&acc_empty[b]);                  // this warp's quadrant of accumulator b is free again
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
+  }
+}
+
 // x -> hi (low 13 mantissa bits cleared) and lo = x - hi; optional transpose: out[c, r] = split(src[r, c])
 __global__ void tf32_split_kernel(const float* __restrict__ src, int64_t ld_src, int32_t rows, int32_t cols, int transpose,
                                   float* __restrict__ hi, float* __restrict__ lo, int64_t ld_out) {
@@ -615,8 +844,47 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
     HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
+  // persistent variant (default; HL_GEMM_PERSISTENT=0 selects the one-tile-per-CTA kernel): needs the A operand in tensor
+  // memory and two accumulators + the A slots inside the 512 TMEM columns
+  static int persistent = -1;
+  if (persistent < 0) { const char* e = getenv("HL_GEMM_PERSISTENT"); persistent = e ? atoi(e) : 1; }
+  // ... and more tiles than the one-tile kernel keeps resident at once (2 CTAs per SM): below that every tile of the
+  // one-tile kernel starts immediately, while 148 persistent CTAs would walk ceil(tiles / 148) tiles one after another
+  // (measured: [24144,64] x [64,64] 5.6 vs 6.4 us, [24144,256] x [256,256] 25.2 vs 18.4 us)
+  if (persistent && use_ts && bn <= 128 && (persistent == 2 || ctas > 2 * 148)) {
+    const int acc_stride = (bn + 31) / 32 * 32;
+    int ps = (int)((227 * 1024 - 1024 - 4 * 32 * kPsPitch * 4 - 256) / stage_bytes);
+    if (ps > 6) ps = 6;
+    while (ps > 2 && 2 * acc_stride + 64 * ps > 512) --ps;
+    if (ps > num_kb && num_kb >= 2) ps = num_kb;
+    if (ps >= 2 && 2 * acc_stride + 64 * ps <= 512) {
+      int cols = 32;
+      while (cols < 2 * acc_stride + 64 * ps) cols <<= 1;
+      const size_t smem_ps = (size_t)ps * stage_bytes + 4 * 32 * kPsPitch * 4 + (3 * ps + 5) * sizeof(uint64_t) + 1024;
+      CUtensorMap pa, pbh, pbl, pa2;
+      if (!make_map(&pa, A, M, K, lda, kGmBM) || !make_map(&pbh, Bhi, N, Ktot, ldb, bn) || !make_map(&pbl, Blo, N, Ktot, ldb, bn))
+        return 1;
+      if (K2 > 0) { if (!make_map(&pa2, A2, M, K2, lda2, kGmBM)) return 1; }
+      else pa2 = pa;
+      static DeviceOnce configured_ps;
+      if (configured_ps.need())
+        HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      GemmParams Q;
+      Q.M = M; Q.N = N; Q.K = Ktot; Q.bn = bn; Q.stages = ps; Q.tmem_cols = cols;
+      Q.bias = bias; Q.C = C; Q.ldc = ldc; Q.accumulate = accumulate; Q.k_per_split = 0; Q.split_stride = 0;
+      Q.tmem_a_col = 2 * acc_stride; Q.colsum_ws = nullptr; Q.conv_groups = 1;
+      Q.kb_first = K2 > 0 ? kb_first : 0x7fffffff;
+      Q.tiles_n = ntiles; Q.num_tiles = ((M + kGmBM - 1) / kGmBM) * ntiles; Q.acc_stride = acc_stride;
+      const int sms = device_sm_count();
+      const int grid_ps = Q.num_tiles < sms ? Q.num_tiles : sms;
+      gemm_tf32x3_persistent_kernel<<<grid_ps, kPsThreads, smem_ps, as_stream(stream)>>>(pa, pbh, pbl, pa2, Q);
+      HL_LAUNCH_CHECK("gemm_tf32x3_persistent_kernel");
+      return HL_OK;
+    }
+  }
   GemmParams P;
   P.M = M; P.N = N; P.K = Ktot; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
+  P.num_tiles = 0; P.tiles_n = 1; P.acc_stride = 0;
   P.bias = bias; P.C = C; P.ldc = ldc; P.accumulate = accumulate; P.k_per_split = 0; P.split_stride = 0;
   P.tmem_a_col = tmem_a_col; P.colsum_ws = nullptr; P.conv_groups = 1;
   P.kb_first = K2 > 0 ? kb_first : 0x7fffffff;
@@ -779,6 +1047,7 @@ extern "C" int hl_wgrad_bias_tf32x3(const float* g, int64_t ld_g, const float* x
     HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   GemmParams P;
+  P.num_tiles = 0; P.tiles_n = 1; P.acc_stride = 0;
   P.M = fo; P.N = fi; P.K = nrows; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
   P.bias = nullptr; P.C = reinterpret_cast<float*>(workspace); P.ldc = fi; P.accumulate = 0;
   P.k_per_split = k_per_split; P.split_stride = (int64_t)fo * fi; P.tmem_a_col = tmem_a_col;
