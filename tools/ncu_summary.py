@@ -8,7 +8,9 @@ rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
 want = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
+        "lts__t_sector_hit_rate.pct",
         "l1tex__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
