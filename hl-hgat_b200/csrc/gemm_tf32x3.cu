@@ -962,7 +962,20 @@ gm_split_reduce_kernel(const float* __restrict__ partial, int32_t splits, int64_
 static int wgrad_tc_splits(int32_t nrows, int tiles) {
   static int waves = 0;
   if (waves == 0) { const char* e = getenv("HL_WGRAD_WAVES"); waves = e ? atoi(e) : 1; if (waves < 1 || waves > 4) waves = 1; }
-  int s = (waves * 148) / tiles;
+  static int ctas = -1;                                 // CTAs one weight-gradient launch spreads over (tiles x splits)
+  if (ctas < 0) { const char* e = getenv("HL_WGRAD_CTAS"); ctas = e ? atoi(e) : 148; if (ctas < 1) ctas = 148; }
+  int s = (waves * ctas) / tiles;
+  // Weight gradients run on auxiliary streams beside the critical chain of the step; filling all 148 SMs with them takes
+  // SMs from that chain and multiplies the partial tiles the reduce has to read.  Measured inside the ZINC step: 148 CTAs
+  // per launch 4.77 ms, at most 16 row splits per tile 4.57 ms (8: 5.04 ms -- then the weight gradients themselves become
+  // the tail).  Long batches keep more splits so that no CTA walks more than ~4096 rows.  HL_WGRAD_SPLIT_CAP overrides.
+  static int cap = -1;
+  if (cap < 0) { const char* e = getenv("HL_WGRAD_SPLIT_CAP"); cap = e ? atoi(e) : 16; }
+  if (cap > 0) {
+    const int by_rows = (nrows + 4095) / 4096;
+    const int lim = cap > by_rows ? cap : by_rows;
+    if (s > lim) s = lim;
+  }
   const int max_s = (nrows + 255) / 256;
   if (s > max_s) s = max_s;
   return s < 1 ? 1 : s;

@@ -92,6 +92,8 @@ def poly_basis_bwd(family, K, ops, g0s, gts, width):
         N.check(L.hl_poly_basis_bwd(family, K, sides, len(csr), width, N.stream_ptr()), "hl_poly_basis_bwd")
 
 
+import os as _os
+_EXPERIMENT_SKIP_WGRAD = _os.environ.get("HL_EXPERIMENT_SKIP_WGRAD") == "1"
 _GEMM_MODE = {"tensor": True}
 
 
@@ -316,6 +318,8 @@ def wgrad(g, x, out=None, accumulate=False, bias_out=None, bias_accumulate=False
     if out is None:
         out = torch.empty((fo, fi), dtype=torch.float32, device=g.device)
         accumulate = False
+    if _EXPERIMENT_SKIP_WGRAD:                   # timing experiment only (HL_EXPERIMENT_SKIP_WGRAD=1): gradients are garbage
+        return out
     acc = 1 if accumulate else 0
     done = False
     if _GEMM_MODE["tensor"]:
