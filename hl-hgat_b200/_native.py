@@ -76,6 +76,9 @@ _SIGNATURES = {
     "hl_wgrad_tf32x3_workspace": (_sz, [_i32, _i32, _i32]),
     "hl_wgrad_tf32x3": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, C.c_int, _vp, _sz, _vp]),
     "hl_wgrad_bias_tf32x3": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, C.c_int, _vp, C.c_int, _vp, _sz, _vp]),
+    "hl_wgrad2_tf32x3_workspace": (_sz, [_i32, _i32, _i32]),
+    "hl_wgrad2_bias_tf32x3": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _i64, C.c_int, _vp, C.c_int,
+                                        _vp, _sz, _vp]),
     "hl_wgrad_workspace": (_sz, [_i32, _i32, _i32]),
     "hl_wgrad": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, C.c_int, _vp, _sz, _vp]),
     "hl_colsum_workspace": (_sz, [_i32, _i32]),

@@ -132,6 +132,7 @@ struct GemmParams {
   float* colsum_ws;         // wgrad TS: per-split column sums of G, [splits][M] (the bias gradient falls out of the A pass)
   int32_t num_tiles, tiles_n;   // persistent kernel: output tiles in total / along N
   int32_t acc_stride;           // persistent kernel: TMEM columns between the two accumulators
+  int32_t x_tiles_each;         // wgrad with TWO X operands (map_bhi, map_blo): column tiles per operand (0 = one operand)
 };
 
 // MODE 0: C = A[M,K] B[N,K]^T, both K-major, B pre-split (map_b = hi, map_b2 = lo).
@@ -160,7 +161,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + 1);
 
   const int m0 = blockIdx.x * kGmBM;
-  const int n0 = blockIdx.y * bn;
+  // weight gradient of two activations that share g (dW = g^T [X1 | X2]): column tiles 0 .. x_tiles_each-1 read X1, the rest X2
+  const int grp = (MODE == 1 && P.x_tiles_each > 0) ? (int)blockIdx.y / P.x_tiles_each : 0;
+  const int n0 = ((int)blockIdx.y - grp * (MODE == 1 ? P.x_tiles_each : 0)) * bn;       // column inside the operand
+  const int c_off = grp * P.N;                                                          // column of the operand in the output plane
   const int k_begin = MODE == 1 ? (int)blockIdx.z * P.k_per_split : 0;
   const int k_end = MODE == 1 ? min(P.K, k_begin + P.k_per_split) : P.K;
   const int num_kb = k_end > k_begin ? (k_end - k_begin + kGmBK - 1) / kGmBK : 0;
@@ -210,8 +214,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           if (TS) gm_tma_load_2d(st, &map_a, &full_bar[s], m0, row);       // plain [32 k-rows][128 m] tile for the converters
           else
             for (int j = 0; j < kGmBM / 32; ++j) gm_tma_load_2d(st + j * 4096, &map_a, &full_bar[s], m0 + 32 * j, row);
+          const CUtensorMap* mx = grp ? &map_blo : &map_bhi;
           for (int j = 0; j < bn / 32; ++j)
-            gm_tma_load_2d(st + b_off + j * 4096, &map_bhi, &full_bar[s], n0 + 32 * j, row);
+            gm_tma_load_2d(st + b_off + j * 4096, mx, &full_bar[s], n0 + 32 * j, row);
         }
       }
     }
@@ -404,7 +409,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rr = m0 + quad * 32 + it * 4 + sub_row;
-            old[it] = (col_ok && rr < P.M) ? *reinterpret_cast<const float4*>(Cbase + (int64_t)rr * P.ldc + col)
+            old[it] = (col_ok && rr < P.M) ? *reinterpret_cast<const float4*>(Cbase + (int64_t)rr * P.ldc + c_off + col)
                                            : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
@@ -428,14 +433,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           float4 v = *reinterpret_cast<const float4*>(stage_tile + lr * kPitch + sub_col);
           v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
           if (P.accumulate) { v.x += old[it].x; v.y += old[it].y; v.z += old[it].z; v.w += old[it].w; }
-          if (col_ok && rr < P.M) *reinterpret_cast<float4*>(Cbase + (int64_t)rr * P.ldc + col) = v;
+          if (col_ok && rr < P.M) *reinterpret_cast<float4*>(Cbase + (int64_t)rr * P.ldc + c_off + col) = v;
         }
         __syncwarp();                                                 // the staging tile is reused by the next chunk
         continue;
       }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (row < P.M) {                                                // unaligned output: element-wise
-        float* crow = Cbase + (int64_t)row * P.ldc + n0 + c;
+        float* crow = Cbase + (int64_t)row * P.ldc + c_off + n0 + c;
         for (int j = 0; j < 32; ++j) {
           const int col = n0 + c + j;
           if (col >= P.N || c + j >= bn) break;                    // tile overhang / columns past this CTA's bn
@@ -874,6 +879,7 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
       Q.bias = bias; Q.C = C; Q.ldc = ldc; Q.accumulate = accumulate; Q.k_per_split = 0; Q.split_stride = 0;
       Q.tmem_a_col = 2 * acc_stride; Q.colsum_ws = nullptr; Q.conv_groups = 1;
       Q.kb_first = K2 > 0 ? kb_first : 0x7fffffff;
+      Q.x_tiles_each = 0;
       Q.tiles_n = ntiles; Q.num_tiles = ((M + kGmBM - 1) / kGmBM) * ntiles; Q.acc_stride = acc_stride;
       const int sms = device_sm_count();
       const int grid_ps = Q.num_tiles < sms ? Q.num_tiles : sms;
@@ -884,7 +890,7 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
   }
   GemmParams P;
   P.M = M; P.N = N; P.K = Ktot; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
-  P.num_tiles = 0; P.tiles_n = 1; P.acc_stride = 0;
+  P.num_tiles = 0; P.tiles_n = 1; P.acc_stride = 0; P.x_tiles_each = 0;
   P.bias = bias; P.C = C; P.ldc = ldc; P.accumulate = accumulate; P.k_per_split = 0; P.split_stride = 0;
   P.tmem_a_col = tmem_a_col; P.colsum_ws = nullptr; P.conv_groups = 1;
   P.kb_first = K2 > 0 ? kb_first : 0x7fffffff;
@@ -900,12 +906,15 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
 __global__ void __launch_bounds__(256)
 gm_split_reduce_kernel(const float* __restrict__ partial, int32_t splits, int64_t split_stride, int32_t fo,
                        int32_t fi, float* __restrict__ dw, int64_t ld_dw, int accumulate,
-                       const float* __restrict__ cs_partial, float* __restrict__ dbias, int accumulate_bias) {
+                       const float* __restrict__ cs_partial, float* __restrict__ dbias, int accumulate_bias,
+                       float* __restrict__ dw2, int64_t ld_dw2, int32_t fi_first) {
+  // fi: columns of a partial plane; with dw2 the plane is [dW1 (fi_first columns) | dW2] and goes to two destinations
   const int64_t n4 = ((int64_t)fo * fi) >> 2;                      // fi % 32 == 0: rows never straddle a float4
   const int64_t c4 = dbias ? (fo >> 2) : 0;                         // + the [splits][fo] column sums of G (bias gradient)
   const int64_t tot4 = n4 + c4;
   const int sub = threadIdx.x & 7;
-  const bool vec_out = (ld_dw % 4 == 0) && ((reinterpret_cast<uintptr_t>(dw) & 15) == 0);
+  const bool vec_out = (ld_dw % 4 == 0) && ((reinterpret_cast<uintptr_t>(dw) & 15) == 0) &&
+                       (!dw2 || ((ld_dw2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(dw2) & 15) == 0)));
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < ((tot4 + 3) & ~(int64_t)3);
        i += ((int64_t)gridDim.x * blockDim.x) >> 3) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -942,7 +951,7 @@ gm_split_reduce_kernel(const float* __restrict__ partial, int32_t splits, int64_
     if (sub == 0 && i < n4) {
       const int64_t e = i << 2;
       const int64_t o = e / fi, c = e - o * fi;
-      float* q = dw + o * ld_dw + c;
+      float* q = (dw2 && c >= fi_first) ? dw2 + o * ld_dw2 + (c - fi_first) : dw + o * ld_dw + c;
       if (vec_out) {
         float4* q4 = reinterpret_cast<float4*>(q);
         if (accumulate) { const float4 t = *q4; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
@@ -1024,19 +1033,29 @@ extern "C" int hl_wgrad_tf32x3(const float* g, int64_t ld_g, const float* x, int
 // ... and, when dbias != NULL, dbias[fo] (=|+=) column sums of g in the same two launches: the converter warps that move
 // G^T into tensor memory add up their column as they go.  Returns 2 (dW done, dbias NOT done: use hl_colsum) when the
 // variant in use cannot fold the bias in.
-extern "C" int hl_wgrad_bias_tf32x3(const float* g, int64_t ld_g, const float* x, int64_t ld_x, int32_t nrows, int32_t fo,
-                                    int32_t fi, float* dw, int64_t ld_dw, int accumulate, float* dbias, int accumulate_bias,
-                                    void* workspace, size_t workspace_bytes, hl_stream_t stream) {
+// nx = 2 (x2 != NULL): two activations of the same shape that share g -- dW1 = g^T x1, dW2 = g^T x2 from ONE launch (column
+// tiles 0 .. ntiles-1 read x1, the rest x2; the partial planes are [fo][2 fi]) and ONE reduce with two destinations.
+static int wgrad_launch(const float* g, int64_t ld_g, const float* x, int64_t ld_x, const float* x2, int64_t ld_x2,
+                        int32_t nrows, int32_t fo, int32_t fi, float* dw, int64_t ld_dw, float* dw2, int64_t ld_dw2,
+                        int accumulate, float* dbias, int accumulate_bias, void* workspace, size_t workspace_bytes,
+                        hl_stream_t stream) {
   using namespace hl;
-  if (nrows < 0 || fo < 1 || fi < 1 || !dw) return HL_ERR_INVALID;
+  const int nx = x2 ? 2 : 1;
+  if (nrows < 0 || fo < 1 || fi < 1 || !dw || (x2 && !dw2)) return HL_ERR_INVALID;
   if (nrows > 0 && (!g || !x)) return HL_ERR_INVALID;
   if (ld_g % 4 != 0 || ld_x % 4 != 0 || !aligned_to(g, 16) || !aligned_to(x, 16)) return 1;
+  if (x2 && (ld_x2 % 4 != 0 || !aligned_to(x2, 16))) return 1;
   if (fo % 4 != 0 || fi % 32 != 0 || nrows < 512) return 1;
-  if (!workspace || workspace_bytes < hl_wgrad_tf32x3_workspace(nrows, fo, fi)) return HL_ERR_WORKSPACE;
   const int ntiles = wgrad_ntiles(fi);
   const int bn = ((fi + ntiles - 1) / ntiles + 31) / 32 * 32;     // multiple of 32: whole {32 x 32} boxes
+  const int mtiles = (fo + kGmBM - 1) / kGmBM;
+  const int splits = wgrad_tc_splits(nrows, mtiles * ntiles * nx);
+  const int64_t fi_tot = (int64_t)fi * nx;
+  const size_t need = align_up((size_t)splits * (size_t)fo * (size_t)fi_tot * sizeof(float), 256) + 2 * (size_t)splits * (size_t)fo * sizeof(float) + 256;
+  if (!workspace || workspace_bytes < need) return HL_ERR_WORKSPACE;
   static int use_ts = -1;
   if (use_ts < 0) { const char* e = getenv("HL_WGRAD_TS"); use_ts = e ? atoi(e) : 1; }
+  if (nx == 2 && !use_ts) return 1;
   const size_t stage_bytes = (use_ts ? 1 : 2) * (size_t)kGmBM * kGmBK * 4 + 2 * (size_t)bn * kGmBK * 4;
   int stages = (int)((200 * 1024) / stage_bytes);
   if (stages > 4) stages = 4;
@@ -1047,40 +1066,67 @@ extern "C" int hl_wgrad_bias_tf32x3(const float* g, int64_t ld_g, const float* x
   int tmem_cols = 32;
   while (tmem_cols < (use_ts ? tmem_a_col + 64 * stages : bn)) tmem_cols <<= 1;
   const size_t smem = stages * stage_bytes + (3 * stages + 2) * sizeof(uint64_t) + 1024;
-  const int mtiles = (fo + kGmBM - 1) / kGmBM;
-  const int splits = wgrad_tc_splits(nrows, mtiles * ntiles);
   const int k_per_split = ((nrows + splits - 1) / splits + 31) / 32 * 32;
 
-  CUtensorMap mg, mx;
+  CUtensorMap mg, mx, mx2;
   if (use_ts ? !make_map(&mg, g, nrows, fo, ld_g, 32, kGmBM, false, true) : !make_map(&mg, g, nrows, fo, ld_g, 32, 32, true)) return 1;
   if (!make_map(&mx, x, nrows, fi, ld_x, 32, 32, true)) return 1;
+  if (x2) { if (!make_map(&mx2, x2, nrows, fi, ld_x2, 32, 32, true)) return 1; }
+  else mx2 = mx;
   static DeviceOnce configured;
   if (configured.need()) {
     HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   GemmParams P;
-  P.num_tiles = 0; P.tiles_n = 1; P.acc_stride = 0;
+  P.num_tiles = 0; P.tiles_n = 1; P.acc_stride = 0; P.x_tiles_each = x2 ? ntiles : 0;
   P.M = fo; P.N = fi; P.K = nrows; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
-  P.bias = nullptr; P.C = reinterpret_cast<float*>(workspace); P.ldc = fi; P.accumulate = 0;
-  P.k_per_split = k_per_split; P.split_stride = (int64_t)fo * fi; P.tmem_a_col = tmem_a_col;
+  P.bias = nullptr; P.C = reinterpret_cast<float*>(workspace); P.ldc = fi_tot; P.accumulate = 0;
+  P.k_per_split = k_per_split; P.split_stride = (int64_t)fo * fi_tot; P.tmem_a_col = tmem_a_col;
   const bool fold_bias = dbias && use_ts;
   float* cs_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) +
-                                          align_up((size_t)splits * (size_t)fo * (size_t)fi * sizeof(float), 256));
+                                          align_up((size_t)splits * (size_t)fo * (size_t)fi_tot * sizeof(float), 256));
   // two converter groups alternate over the ring stages: a group must meet every phase of the barriers it waits on, so
   // the stage count has to be even (with 3 stages group 0 would see stage 0 at rounds 0, 2, 4, ... and a parity wait
   // cannot tell round 2 from round 0)
   static int max_groups = 0;
   if (max_groups == 0) { const char* e = getenv("HL_WGRAD_GROUPS"); max_groups = e ? atoi(e) : 2; if (max_groups < 1 || max_groups > 2) max_groups = 2; }
   P.colsum_ws = fold_bias ? cs_ws : nullptr; P.conv_groups = (use_ts && max_groups == 2 && stages % 2 == 0) ? 2 : 1;
-  dim3 grid(mtiles, ntiles, splits);
+  dim3 grid(mtiles, ntiles * nx, splits);
   P.kb_first = 0;
-  if (use_ts) gemm_tf32x3_kernel<1, 1><<<grid, 64 + P.conv_groups * kGmConvThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
+  if (use_ts) gemm_tf32x3_kernel<1, 1><<<grid, 64 + P.conv_groups * kGmConvThreads, smem, as_stream(stream)>>>(mg, mx, mx2, mx, P);
   else gemm_tf32x3_kernel<1, 0><<<grid, 64 + kGmConvThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
   HL_LAUNCH_CHECK("gemm_tf32x3_kernel<wgrad>");
-  const int64_t n = (int64_t)fo * fi;
+  const int64_t n = (int64_t)fo * fi_tot;
   gm_split_reduce_kernel<<<(int)(((n + (fold_bias ? fo : 0)) * 2 + 255) / 256), 256, 0, as_stream(stream)>>>(
-      P.C, splits, P.split_stride, fo, fi, dw, ld_dw, accumulate, cs_ws, fold_bias ? dbias : nullptr, accumulate_bias);
+      P.C, splits, P.split_stride, fo, (int32_t)fi_tot, dw, ld_dw, accumulate, cs_ws, fold_bias ? dbias : nullptr, accumulate_bias,
+      dw2, ld_dw2, fi);
   HL_LAUNCH_CHECK("gm_split_reduce_kernel");
   return (dbias && !fold_bias) ? 2 : HL_OK;
+}
+
+extern "C" int hl_wgrad_bias_tf32x3(const float* g, int64_t ld_g, const float* x, int64_t ld_x, int32_t nrows, int32_t fo,
+                                    int32_t fi, float* dw, int64_t ld_dw, int accumulate, float* dbias, int accumulate_bias,
+                                    void* workspace, size_t workspace_bytes, hl_stream_t stream) {
+  return wgrad_launch(g, ld_g, x, ld_x, nullptr, 0, nrows, fo, fi, dw, ld_dw, nullptr, 0, accumulate, dbias, accumulate_bias,
+                      workspace, workspace_bytes, stream);
+}
+
+extern "C" size_t hl_wgrad2_tf32x3_workspace(int32_t nrows, int32_t fo, int32_t fi) {
+  if (nrows < 0 || fo < 1 || fi < 1) return 0;
+  const int ntiles = wgrad_ntiles(fi);
+  const int tiles = ((fo + hl::kGmBM - 1) / hl::kGmBM) * ntiles * 2;
+  const size_t splits = (size_t)wgrad_tc_splits(nrows, tiles);
+  return hl::align_up(splits * (size_t)fo * (size_t)fi * 2 * sizeof(float), 256) + 2 * splits * (size_t)fo * sizeof(float) + 256;
+}
+
+// dW1 (=|+=) g^T x1 and dW2 (=|+=) g^T x2 (x1, x2: [R, fi], the same g [R, fo]) from one launch + one reduce; dbias as above.
+// Returns 1 when the shape is unsupported (caller issues two single launches).
+extern "C" int hl_wgrad2_bias_tf32x3(const float* g, int64_t ld_g, const float* x1, int64_t ld_x1, const float* x2, int64_t ld_x2,
+                                     int32_t nrows, int32_t fo, int32_t fi, float* dw1, int64_t ld_dw1, float* dw2,
+                                     int64_t ld_dw2, int accumulate, float* dbias, int accumulate_bias, void* workspace,
+                                     size_t workspace_bytes, hl_stream_t stream) {
+  if (!x2 || !dw2) return HL_ERR_INVALID;
+  return wgrad_launch(g, ld_g, x1, ld_x1, x2, ld_x2, nrows, fo, fi, dw1, ld_dw1, dw2, ld_dw2, accumulate, dbias, accumulate_bias,
+                      workspace, workspace_bytes, stream);
 }

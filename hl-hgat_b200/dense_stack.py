@@ -271,9 +271,8 @@ class _StackLinear(torch.autograd.Function):
                 gbias = tgt_b if tgt_b is not None else torch.empty(weight.shape[0], dtype=torch.float32, device=g.device)
             with F_hl._wgrad_lane(tgt is not None, g, xa, xb):
                 gw = torch.empty_like(weight) if tgt is None else tgt
-                F_hl.wgrad(g, xa, gw[:, :d], accumulate=tgt is not None, bias_out=gbias if fold else None,
-                           bias_accumulate=tgt_b is not None)
-                F_hl.wgrad(g, xb, gw[:, d:], accumulate=tgt is not None)
+                F_hl.wgrad2(g, xa, xb, gw[:, :d], gw[:, d:], accumulate=tgt is not None, bias_out=gbias if fold else None,
+                            bias_accumulate=tgt_b is not None)
             if tgt is not None:
                 gw = None
             if fold:

@@ -94,6 +94,7 @@ def poly_basis_bwd(family, K, ops, g0s, gts, width):
 
 import os as _os
 _EXPERIMENT_SKIP_WGRAD = _os.environ.get("HL_EXPERIMENT_SKIP_WGRAD") == "1"
+_WGRAD2 = _os.environ.get("HL_WGRAD2", "1") != "0"          # two weight gradients sharing g in one launch (A/B switch)
 _GEMM_MODE = {"tensor": True}
 
 
@@ -343,6 +344,35 @@ def wgrad(g, x, out=None, accumulate=False, bias_out=None, bias_accumulate=False
     return out
 
 
+def wgrad2(g, x1, x2, out1, out2, accumulate=False, bias_out=None, bias_accumulate=False):
+    """out1 (=|+=) g^T x1 and out2 (=|+=) g^T x2 for two activations of the same shape that share g: ONE tensor-core
+    launch and one reduce (`hl_wgrad2_bias_tf32x3`) when the shape allows, else two `wgrad` calls."""
+    L = N.lib()
+    done = False
+    if _GEMM_MODE["tensor"] and not _EXPERIMENT_SKIP_WGRAD and _WGRAD2 and x1.shape == x2.shape:
+        g2, ldg = N.row_major(g)
+        a, lda = N.row_major(x1)
+        b, ldb = N.row_major(x2)
+        R, fo = g2.shape
+        fi = a.shape[1]
+        nb = L.hl_wgrad2_tf32x3_workspace(R, fo, fi)
+        ws = torch.empty(nb, dtype=torch.uint8, device=g.device)
+        acc = 1 if accumulate else 0
+        rc = L.hl_wgrad2_bias_tf32x3(g2.data_ptr(), ldg, a.data_ptr(), lda, b.data_ptr(), ldb, R, fo, fi, out1.data_ptr(), out1.stride(0),
+                                     out2.data_ptr(), out2.stride(0), acc, N.ptr(bias_out), 1 if bias_accumulate else 0,
+                                     ws.data_ptr(), nb, N.stream_ptr())
+        if rc == 0 or rc == 2:
+            done = True
+            if rc == 2 and bias_out is not None:
+                _colsum_into(g2, ldg, bias_out, bias_accumulate)
+        elif rc != 1:
+            N.check(rc, "hl_wgrad2_bias_tf32x3")
+    if not done:
+        wgrad(g, x1, out1, accumulate=accumulate, bias_out=bias_out, bias_accumulate=bias_accumulate)
+        wgrad(g, x2, out2, accumulate=accumulate)
+    return out1, out2
+
+
 def _colsum_into(g, ldg, out, accumulate):
     L = N.lib()
     R, f = g.shape
@@ -399,10 +429,14 @@ class _Linear(torch.autograd.Function):
                 gbias = tgt_b if tgt_b is not None else torch.empty(weight.shape[0], dtype=torch.float32, device=g.device)
             with _wgrad_lane(tgt is not None, g, xa, xb):
                 gw = torch.empty_like(weight) if tgt is None else tgt
-                wgrad(g, xa, gw[:, :d], accumulate=tgt is not None, bias_out=gbias if fold else None,
-                      bias_accumulate=tgt_b is not None)
-                if xb is not None:
-                    wgrad(g, xb, gw[:, d:], accumulate=tgt is not None)
+                if xb is not None and xb.shape == xa.shape:
+                    wgrad2(g, xa, xb, gw[:, :d], gw[:, d:], accumulate=tgt is not None, bias_out=gbias if fold else None,
+                           bias_accumulate=tgt_b is not None)
+                else:
+                    wgrad(g, xa, gw[:, :d], accumulate=tgt is not None, bias_out=gbias if fold else None,
+                          bias_accumulate=tgt_b is not None)
+                    if xb is not None:
+                        wgrad(g, xb, gw[:, d:], accumulate=tgt is not None)
             if tgt is not None:
                 gw = None
             if fold:
@@ -535,24 +569,36 @@ class _PolyConv(torch.autograd.Function):
         want_bias = ctx.has_bias and ctx.needs_input_grad[1]
         tgt_b = _grad_target(ctx.params[0]) if want_bias else None
         gb = None
-        gws = []
-        for k in range(K):
-            if ctx.needs_input_grad[5 + k]:
-                src = x if k == 0 else t[k - 1]
-                tgt = _grad_target(ctx.params[1][k])
-                fold = want_bias and (tgt is None) == (tgt_b is None) and g.shape[0] == src.numel() // inner
-                if fold:                                   # bias gradient rides on this weight-gradient launch
-                    gb = tgt_b if tgt_b is not None else torch.empty(g.shape[1], dtype=torch.float32, device=g.device)
-                with _wgrad_lane(tgt is not None, g, src):
+        gws = [None] * K
+        k = 0
+        while k < K:
+            if not ctx.needs_input_grad[5 + k]:
+                k += 1
+                continue
+            src = x if k == 0 else t[k - 1]
+            tgt = _grad_target(ctx.params[1][k])
+            fold = want_bias and (tgt is None) == (tgt_b is None) and g.shape[0] == src.numel() // inner
+            if fold:                                   # bias gradient rides on this weight-gradient launch
+                gb = tgt_b if tgt_b is not None else torch.empty(g.shape[1], dtype=torch.float32, device=g.device)
+            # two consecutive orders share g: one launch for both weight gradients (hl_wgrad2_bias_tf32x3)
+            pair = k + 1 < K and ctx.needs_input_grad[6 + k] and (_grad_target(ctx.params[1][k + 1]) is None) == (tgt is None)
+            with _wgrad_lane(tgt is not None, g, src, t[k] if pair else None):
+                if pair:
+                    tgt2 = _grad_target(ctx.params[1][k + 1])
+                    o1 = tgt if tgt is not None else torch.empty_like(weights[k])
+                    o2 = tgt2 if tgt2 is not None else torch.empty_like(weights[k + 1])
+                    wgrad2(g, src.view(-1, inner), t[k].view(-1, inner), o1, o2, accumulate=tgt is not None,
+                           bias_out=gb if fold else None, bias_accumulate=tgt_b is not None)
+                    gws[k], gws[k + 1] = (None, None) if tgt is not None else (o1, o2)
+                else:
                     gw = wgrad(g, src.view(-1, inner), out=tgt, accumulate=tgt is not None, bias_out=gb if fold else None,
                                bias_accumulate=tgt_b is not None)
-                if fold:
-                    want_bias = False
-                    if tgt_b is not None:
-                        gb = None
-                gws.append(None if tgt is not None else gw)
-            else:
-                gws.append(None)
+                    gws[k] = None if tgt is not None else gw
+            if fold:
+                want_bias = False
+                if tgt_b is not None:
+                    gb = None
+            k += 2 if pair else 1
         if want_bias:
             with _wgrad_lane(tgt_b is not None, g):
                 gb = colsum(g, out=tgt_b)

@@ -363,6 +363,14 @@ int hl_wgrad_tf32x3(const float* g, int64_t ld_g, const float* x, int64_t ld_x, 
 int hl_wgrad_bias_tf32x3(const float* g, int64_t ld_g, const float* x, int64_t ld_x, int32_t nrows, int32_t fo, int32_t fi,
                          float* dw, int64_t ld_dw, int accumulate, float* dbias /* nullable */, int accumulate_bias,
                          void* workspace, size_t workspace_bytes, hl_stream_t stream);
+/* Two activations of the same shape sharing g: dW1 (=|+=) g^T x1, dW2 (=|+=) g^T x2 from ONE tensor-core launch and one
+ * reduce (the two halves of the first NodeEdgeInt Linear, lib/Hodge_Cheb_Conv.py:307-308; consecutive orders of a conv,
+ * :497,509).  Returns 1 when the shape is unsupported. */
+size_t hl_wgrad2_tf32x3_workspace(int32_t nrows, int32_t fo, int32_t fi);
+int hl_wgrad2_bias_tf32x3(const float* g, int64_t ld_g, const float* x1, int64_t ld_x1, const float* x2, int64_t ld_x2,
+                          int32_t nrows, int32_t fo, int32_t fi, float* dw1, int64_t ld_dw1, float* dw2, int64_t ld_dw2,
+                          int accumulate, float* dbias /* nullable */, int accumulate_bias, void* workspace,
+                          size_t workspace_bytes, hl_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
  * Weight and bias gradients of the dense layers as deterministic split-row reductions.

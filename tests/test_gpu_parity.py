@@ -468,3 +468,30 @@ def test_bn_running_stats_match_torch():
     close(mine.running_mean, ref.running_mean)
     close(mine.running_var, ref.running_var)
     assert int(mine.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("R,fo,fi", [(24001, 64, 64), (24144, 256, 704), (5000, 128, 192), (3000, 256, 256), (700, 64, 96), (300, 64, 64)])
+def test_wgrad2_two_operands_one_launch(R, fo, fi):
+    """dW1 = g^T x1 and dW2 = g^T x2 from one launch + one reduce with two destinations (the two halves of the first
+    NodeEdgeInt Linear read from strided dense-connection buffers; consecutive orders of a conv): fp64 parity, bias fold,
+    accumulation, determinism; shapes the grouped kernel does not take fall back to two single launches."""
+    torch.manual_seed(R + fi)
+    g = torch.randn(R, fo, device=DEV) + 0.1
+    wide = torch.randn(R, 2 * fi + 64, device=DEV)
+    x1, x2 = wide[:, :fi], wide[:, fi + 32:2 * fi + 32]                # strided views, like the stack buffers
+    r1, r2, rb = g.double().t() @ x1.double(), g.double().t() @ x2.double(), g.double().sum(0)
+    w = torch.full((fo, 2 * fi), float("nan"), device=DEV)              # one weight matrix [fo, 2 fi]: the MLP case
+    db = torch.full((fo,), float("nan"), device=DEV)
+    F_hl.wgrad2(g, x1, x2, w[:, :fi], w[:, fi:], bias_out=db)
+    scale = float(max(r1.abs().max(), r2.abs().max()))
+    assert float((w[:, :fi].double() - r1).abs().max()) < 1e-4 * scale
+    assert float((w[:, fi:].double() - r2).abs().max()) < 1e-4 * scale
+    assert float((db.double() - rb).abs().max()) < 1e-5 * float(rb.abs().max())
+    a1, a2 = torch.empty(fo, fi, device=DEV), torch.empty(fo, fi, device=DEV)   # two separate parameters: the conv case
+    F_hl.wgrad2(g, x1, x2, a1, a2)
+    assert torch.equal(a1, w[:, :fi]) and torch.equal(a2, w[:, fi:])             # deterministic, destination-independent
+    acc1, acc2, accb = torch.randn(fo, fi, device=DEV), torch.randn(fo, fi, device=DEV), torch.randn(fo, device=DEV)
+    want1, want2, wantb = acc1.double() + r1, acc2.double() + r2, accb.double() + rb
+    F_hl.wgrad2(g, x1, x2, acc1, acc2, accumulate=True, bias_out=accb, bias_accumulate=True)
+    assert float((acc1.double() - want1).abs().max()) < 1e-4 * scale and float((acc2.double() - want2).abs().max()) < 1e-4 * scale
+    assert float((accb.double() - wantb).abs().max()) < 1e-5 * float(rb.abs().max())
