@@ -256,7 +256,7 @@ def run_ours(args, world, rank, local):
     import hlhgat_b200
     from hlhgat_b200 import _native as N
     from hlhgat_b200.lib import Hodge_ST_Model as M
-    from hlhgat_b200.parallel import FlatGradBucket, broadcast_parameters
+    from hlhgat_b200.parallel import FlatGradBucket, FlatAdam, broadcast_parameters
     from hlhgat_b200.synthetic import batch_to
     from hlhgat_b200.workloads import WORKLOADS
     from hlhgat_b200.training import Capacity, pad_batch, pad_levels, padded_nbytes, GraphedTrainStep, BatchPrefetcher
@@ -279,7 +279,10 @@ def run_ours(args, world, rank, local):
     model = getattr(M, wl.model)(**wl.ctor).to(dev).train()
     broadcast_parameters(model)
     bucket = FlatGradBucket(model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3, fused=True, capturable=True)
+    if args.optimizer == "flat":      # torch.optim.Adam's update rule as one streaming kernel over flat buffers (hl_adam_flat)
+        opt = FlatAdam(bucket, lr=1e-3, weight_decay=1e-3)
+    else:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3, fused=True, capturable=True)
 
     raw = [wl.make(batch_size, 1000 * rank + i) for i in range(args.pool)]
     levels = [[b[l] for b in raw] for l in range(wl.levels)] if wl.levels > 1 else [raw]
@@ -397,6 +400,8 @@ def run_ours(args, world, rank, local):
                                     if args.project_first == "on" else "transfer-then-project (the reference's order)"),
                        "edge_operator": ("L1 applied in factored form diag(2/lambda) B1^T B1 (opt-in, fp32-rounding-equal to the CSR path)"
                                          if factored else "L1 applied from its CSR (bit-exact summation order of the reference)"),
+                       "optimizer": ("Adam(lr 1e-3, weight_decay 1e-3) as one hl_adam_flat launch over flat parameter / gradient / moment "
+                                     "buffers, 1/world_size folded in" if args.optimizer == "flat" else "torch.optim.Adam(fused=True, capturable=True)"),
                        "gemm": "dense Theta/MLP transforms + data/weight gradients: hand-written tcgen05 3xTF32 kernels (fp32-accurate); "
                                "cuBLAS fp32 only for shapes with N % 16 != 0 or unaligned rows (first-layer inputs)"},
             "e2e": {"value": e2e, "unit": "graphs/s", "ms_per_step": ms_e2e / args.steps,
@@ -489,6 +494,9 @@ def main():
     ap.add_argument("--project-first", default="off", choices=["on", "off"],
                     help="NodeEdgeInt applies W_a before the node<->edge transfer when the layer is narrower than the "
                          "dense-connection buffer (transfers move f instead of d columns; fp32-rounding-equal)")
+    ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"],
+                    help="flat: Adam (torch.optim.Adam semantics, lr 1e-3, weight decay 1e-3 as in main_zinc...py:213) as one "
+                         "hand-written kernel over flat parameter / gradient / moment buffers; torch: torch.optim.Adam(fused, capturable)")
     ap.add_argument("--dense-stack", default="on", choices=["on", "off"],
                     help="dense connections in preallocated buffers (no torch.cat, every block transferred to the other simplex "
                          "order once, data gradients accumulated in the GEMM epilogue); off = the reference's cat + full re-transfer")

@@ -85,6 +85,7 @@ _SIGNATURES = {
     "hl_colsum": (C.c_int, [_vp, _i64, _i32, _i32, _vp, C.c_int, _vp, _sz, _vp]),
     "hl_poly_basis_hodge1_fwd": (C.c_int, [C.c_int, C.c_int, C.POINTER(Hodge1Operator), _vp, _i64, _vp, _i64, _i64, _vp, _i32, _vp]),
     "hl_poly_basis_hodge1_bwd": (C.c_int, [C.c_int, C.c_int, C.POINTER(Hodge1Operator), _vp, _i64, _vp, _i64, _i64, _vp, _i32, _vp]),
+    "hl_adam_flat": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
     "hl_eig_pe_workspace": (_sz, [_i64]),
     "hl_eig_pe": (C.c_int, [_vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _i32, _vp, _sz, _vp]),
     "hl_greedy_matching": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhlhgat.so")
-SOURCES = ["api.cu", "poly_spmm.cu", "poly_spmm_staged.cu", "poly_hodge1.cu", "segment.cu", "csr_build.cu", "batchnorm.cu", "construct.cu", "coarsen.cu", "eig_pe.cu", "wgrad.cu", "gemm_tf32x3.cu"]
+SOURCES = ["api.cu", "poly_spmm.cu", "poly_spmm_staged.cu", "poly_hodge1.cu", "segment.cu", "csr_build.cu", "batchnorm.cu", "construct.cu", "coarsen.cu", "eig_pe.cu", "adam.cu", "wgrad.cu", "gemm_tf32x3.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -430,22 +430,26 @@ extern "C" int hl_segment_reduce(const int32_t* rowptr, const int32_t* colidx, i
   V = min(V, vec_for(dst, ld_dst, width, V));
   const int G = group_lanes(width, V);
   const int chunks = (width + V - 1) / V;
-  const int CH = chunks > G ? 2 : 1;
+  int CH = chunks > G ? 2 : 1;
+  // rows of 257-384 floats (the 320-wide dense-connection buffers the attention pooling averages): three chunks per lane keep
+  // the row in ONE lane group instead of a second, mostly idle column tile that repeats all the index work
+  static int use_rows = -1;
+  if (use_rows < 0) { const char* e = getenv("HL_SEG_ROWS"); use_rows = e ? atoi(e) : 8; }
+  const bool rows_variant = use_rows && G >= 16 && V == 4 && nrows >= 4096;
+  if (rows_variant && use_rows >= 8 && chunks > 2 * G && chunks <= 3 * G) CH = 3;
   const int tile_w = G * V * CH;
   dim3 grid((nrows + kSegThreads / G - 1) / (kSegThreads / G), (width + tile_w - 1) / tile_w);
   // row-batched variant (8 rows per lane group; HL_SEG_ROWS=4: 4 rows) whenever a group has the lanes to hold the row
   // pointers; HL_SEG_ROWS=0 selects the per-row kernel for A/B runs.  Measured on the x16 ZINC incidence stack (B200):
   // s2t at F=64 1.87 -> 2.94 TB/s, at F=256 1.97 -> 3.80 TB/s; adjoint of t2s 1.96 -> 3.28 / 2.02 -> 3.98 TB/s
-  static int use_rows = -1;
-  if (use_rows < 0) { const char* e = getenv("HL_SEG_ROWS"); use_rows = e ? atoi(e) : 8; }
-  if (use_rows && G >= 16 && V == 4 && nrows >= 4096) {
+  if (rows_variant) {
     const int RB = use_rows >= 8 ? 8 : 4;
     const int groups = (nrows + RB - 1) / RB;
     dim3 grid_rb((groups + kSegThreads / G - 1) / (kSegThreads / G), (width + tile_w - 1) / tile_w);
 #define HL_SEGR_CASE(CC, RR)                                                                                   \
     segment_reduce_rows_kernel<4, CC, RR><<<grid_rb, kSegThreads, 0, as_stream(stream)>>>(                        \
         rowptr, colidx, nrows, src, ld_src, src_scale, dst, ld_dst, width, G, post, row_scale, cscale)
-    if (RB == 8) { if (CH == 2) HL_SEGR_CASE(2, 8); else HL_SEGR_CASE(1, 8); }
+    if (RB == 8) { if (CH == 3) HL_SEGR_CASE(3, 8); else if (CH == 2) HL_SEGR_CASE(2, 8); else HL_SEGR_CASE(1, 8); }
     else { if (CH == 2) HL_SEGR_CASE(2, 4); else HL_SEGR_CASE(1, 4); }
 #undef HL_SEGR_CASE
     HL_LAUNCH_CHECK("segment_reduce_rows_kernel");

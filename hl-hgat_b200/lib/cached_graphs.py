@@ -9,7 +9,8 @@ stream is decoded WITHOUT importing either: every class that is not a torch tens
 materialised as an inert attribute bag, from which the tensors are lifted into `hlhgat_b200.lib.Hodge_Dataset.PairData`.
 Both PyG layouts are understood -- PyG >= 2.0 (`Data.__dict__ = {'_store': GlobalStorage}` whose state holds
 `_mapping`) and PyG 1.x (the attributes directly in `__dict__`).  No foreign code runs: `find_class` never imports a
-module outside an allow-list (torch rebuild helpers, collections.OrderedDict, numpy array reconstruction).
+module outside an allow-list (torch's tensor rebuild helpers / storage classes / dtypes, collections.OrderedDict, numpy
+array reconstruction) -- anything else in the stream becomes an inert stand-in object.
 """
 import glob
 import os
@@ -24,9 +25,21 @@ from .Hodge_Dataset import PairData, collate
 __all__ = ["load_cached_graph", "CachedGraphs", "ZINC_HG_BM_par1_EigPE", "ZINC_HG_BM_par1_MLGC", "Peptides_Func_EigPE",
            "Peptides_Func_EigPE_MLGC", "TSP_EigPE", "collate"]
 
-_ALLOWED_PREFIXES = ("torch", "collections", "numpy", "_codecs", "builtins", "copyreg")
 _BUILTINS_OK = {"dict", "list", "tuple", "set", "frozenset", "int", "float", "bool", "str", "bytes", "bytearray", "complex",
-                "slice", "range", "object", "getattr"}
+                "slice", "range", "object"}
+_EXACT_OK = {("collections", "OrderedDict"), ("_codecs", "encode"), ("copyreg", "_reconstructor"),
+             ("numpy", "ndarray"), ("numpy", "dtype"), ("numpy.core.multiarray", "_reconstruct"),
+             ("numpy._core.multiarray", "_reconstruct"), ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar")}
+
+
+def _torch_object_ok(obj, name):
+    """What a tensor pickle needs from `torch`: the rebuild helpers, storage classes, dtypes, Size / device -- never an
+    arbitrary callable of the package (torch.load, torch.hub, ... stay unreachable)."""
+    if isinstance(obj, (torch.dtype, torch.layout, torch.memory_format)) or obj in (torch.Size, torch.device, torch.Tensor):
+        return True
+    if isinstance(obj, type) and (name.endswith("Storage") or issubclass(obj, torch.Tensor)):
+        return True
+    return callable(obj) and name.startswith("_rebuild")
 
 
 class _Bag:
@@ -60,8 +73,12 @@ def _bag_class(module, name):
 class _Unpickler(pickle.Unpickler):
     def find_class(self, module, name):
         root = module.split(".")[0]
-        if root in _ALLOWED_PREFIXES and not (root == "builtins" and name not in _BUILTINS_OK):
+        if (module, name) in _EXACT_OK or (module == "builtins" and name in _BUILTINS_OK):
             return super().find_class(module, name)
+        if root == "torch":
+            obj = super().find_class(module, name)
+            if _torch_object_ok(obj, name):
+                return obj
         return _bag_class(module, name)                # torch_geometric.*, lib.Hodge_Dataset.PairData, anything else
 
 

@@ -19,6 +19,8 @@ class FlatGradBucket:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
 
+    pending_scale = 1.0          # set by all_reduce_sum(): the 1 / world_size a FlatAdam step folds into its update
+
     def zero(self):
         self.flat.zero_()
 
@@ -26,6 +28,50 @@ class FlatGradBucket:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             self.flat.div_(dist.get_world_size(group))
+
+    def all_reduce_sum(self, group=None):
+        """SUM only; the division by the world size is left to the optimizer (`FlatAdam.step` reads `pending_scale`)."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.pending_scale = 1.0 / dist.get_world_size(group)
+
+
+class FlatAdam:
+    """torch.optim.Adam semantics (L2 weight decay, bias correction) as ONE streaming kernel over flat buffers
+    (`hl_adam_flat`): the parameters are moved into one contiguous buffer (every `p.data` becomes a view of it -- call
+    this BEFORE the first forward pass, the weight-split plan keys on data pointers), the gradients are the views of
+    `bucket` (a FlatGradBucket over the same parameters, same order), the moments are flat too.  The data-parallel mean is
+    folded in: `step()` scales the (summed) gradients by 1 / world_size, so the bucket only has to all-reduce with SUM.
+    Capturable: the step counter lives on the device."""
+
+    def __init__(self, bucket, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.bucket, self.lr, self.betas, self.eps, self.weight_decay = bucket, lr, betas, eps, weight_decay
+        ps = bucket.params
+        flat = torch.empty_like(bucket.flat)
+        off = 0
+        with torch.no_grad():
+            for p in ps:
+                n = p.numel()
+                flat[off:off + n].copy_(p.data.reshape(-1))
+                p.data = flat[off:off + n].view_as(p)
+                off += n
+        self.flat_params = flat
+        self.exp_avg = torch.zeros_like(flat)
+        self.exp_avg_sq = torch.zeros_like(flat)
+        self.state = torch.zeros(3, dtype=torch.float32, device=flat.device)
+
+    def step(self, grad_scale=None):
+        from . import _native as N
+        if grad_scale is None:
+            grad_scale = self.bucket.pending_scale
+            self.bucket.pending_scale = 1.0
+        N.check(N.lib().hl_adam_flat(self.flat_params.data_ptr(), self.bucket.flat.data_ptr(), self.exp_avg.data_ptr(),
+                                     self.exp_avg_sq.data_ptr(), self.flat_params.numel(), self.state.data_ptr(), self.lr,
+                                     self.betas[0], self.betas[1], self.eps, self.weight_decay, float(grad_scale), N.stream_ptr()),
+                "hl_adam_flat")
+
+    def zero_grad(self, set_to_none=False):
+        self.bucket.zero()
 
 
 def shard_graphs(costs, world_size):

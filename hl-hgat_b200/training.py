@@ -183,8 +183,7 @@ class GraphedTrainStep:
         with torch.cuda.stream(side):
             for _ in range(warmup):                               # eager warm-up on a side stream
                 self._fwd_bwd()
-                self.bucket.all_reduce_mean()
-                self.optimizer.step()
+                self._reduce_and_update()
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
         clear_caches()
@@ -196,13 +195,20 @@ class GraphedTrainStep:
             self._fwd_bwd()
             self.launches_per_step = int(N.lib().hl_launch_count() - before)   # libhlhgat kernels in the graph
             if self.single_graph:
-                self.bucket.all_reduce_mean()
-                self.optimizer.step()
+                self._reduce_and_update()
         if not self.single_graph:
             self.graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_opt, pool=self.graph_fb.pool()):
                 self.optimizer.step()
         clear_caches()
+
+    def _reduce_and_update(self):
+        from .parallel import FlatAdam
+        if isinstance(self.optimizer, FlatAdam) and self.single_graph:
+            self.bucket.all_reduce_sum()          # the 1 / world_size rides on the Adam kernel's gradient scale
+        else:
+            self.bucket.all_reduce_mean()
+        self.optimizer.step()
 
     def _fwd_bwd(self):
         if self.split_plan is None:

@@ -280,6 +280,17 @@ int hl_bn_bwd_apply(const float* x, int64_t ld_x, const float* y, int64_t ld_y, 
                     const int32_t* nvalid, hl_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Adam over flat buffers: one streaming pass over parameters, gradients and both moments (all [n] fp32, 16-byte aligned).
+ * Replaces: torch.optim.Adam(model.parameters(), lr, weight_decay).step() of the training scripts
+ * (main_zinc_HL_HGCNN_dense_int3_pyr.py:213, :150-160) -- same update rule (L2 weight decay added to the gradient,
+ * bias-corrected moments, eps outside the root); `grad_scale` multiplies the gradient first (1 / world_size of the
+ * data-parallel average).  state[3] (device): {step, 1 / (1 - beta1^step), 1 / sqrt(1 - beta2^step)}; the call advances it,
+ * so the optimizer step is capturable into a CUDA graph.
+ * -------------------------------------------------------------------------------------------- */
+int hl_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float* state,
+                 float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, hl_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
  * Eigenvector positional encodings of every graph of a mini-batch.
  * Replaces: `eig_pe(L, k)` = scipy.linalg.eigh of the dense normalised Laplacian + argsort + columns 1 .. k-1
  * (lib/Hodge_Dataset.py:97-112; callers :457-458 ZINC, :586-587 peptides, :846-847 CIFAR10SP) and the dense `eigh`
