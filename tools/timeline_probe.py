@@ -91,6 +91,19 @@ for t, d in pts:
     last = t
     cur += d
 print("\nconcurrency (kernels running at once): " + ", ".join(f"{k}: {v / 1e3:.3f} ms" for k, v in sorted(hist.items())))
+# which kernels run ALONE (nothing overlaps them): candidates for the critical chain / for under-filled SMs
+alone, active, last = collections.Counter(), set(), t0
+for t, d, i in sorted([(e["ts"], 1, i) for i, e in enumerate(step_ev)] + [(e["ts"] + e["dur"], -1, i) for i, e in enumerate(step_ev)]):
+    if t > last and len(active) <= 1:
+        alone[step_ev[next(iter(active))]["name"].split("(")[0][:60] if active else "<idle>"] += t - last
+    last = t
+    if d == 1:
+        active.add(i)
+    else:
+        active.discard(i)
+print(f"\ntime with at most one kernel running: {sum(alone.values()) / 1e3:.3f} ms; by kernel:")
+for nm, t in alone.most_common(14):
+    print(f"{t / 1e3:8.3f} ms  {nm}")
 kt, kn = collections.Counter(), collections.Counter()
 for e in step_ev:
     nm = e["name"].split("(")[0][:70]
