@@ -37,7 +37,13 @@ def _worker(rank, world, init_file, state, out_file):
     bucket = FlatGradBucket(model.parameters())
     bucket.zero()
     torch.nn.functional.l1_loss(model(b), b.y).backward()
+    summed = bucket.flat.clone()
     bucket.all_reduce_mean()
+    # the SUM-only variant leaves the 1 / world_size to the optimizer (parallel.FlatAdam reads `pending_scale`)
+    bucket.flat.copy_(summed)
+    bucket.all_reduce_sum()
+    assert bucket.pending_scale == 1.0 / world
+    bucket.flat.mul_(bucket.pending_scale)
     if rank == 0:
         torch.save(bucket.flat.clone(), out_file)
     dist.barrier()
