@@ -73,6 +73,8 @@ _SIGNATURES = {
     "hl_tf32_split_batch": (C.c_int, [_vp, _i32, _i64, _vp]),
     "hl_gemm_tf32x3": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _i64, C.c_int, _vp]),
     "hl_gemm2_tf32x3": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _i64, C.c_int, _vp]),
+    "hl_gemm_bn_part_floats": (_sz, [_i32, _i32]),
+    "hl_gemm2_bn_tf32x3": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _i64, C.c_int, _vp, _vp, _vp]),
     "hl_wgrad_tf32x3_workspace": (_sz, [_i32, _i32, _i32]),
     "hl_wgrad_tf32x3": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, C.c_int, _vp, _sz, _vp]),
     "hl_wgrad_bias_tf32x3": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, C.c_int, _vp, C.c_int, _vp, _sz, _vp]),
@@ -91,6 +93,7 @@ _SIGNATURES = {
     "hl_greedy_matching": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hl_bn_workspace": (_sz, [_i32, _i32]),
     "hl_bn_act_fwd": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _vp, _i64, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _sz, _vp]),
+    "hl_bn_act_fwd_tiles": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _vp, _i64, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp]),
     "hl_bn_act_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32,
                                 _vp, _i64, _vp, _vp, C.c_int, _vp, _vp, _sz, _vp]),
     "hl_bn_stats": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),

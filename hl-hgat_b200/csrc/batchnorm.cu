@@ -155,6 +155,57 @@ __global__ void bn_stats_final_kernel(const double* __restrict__ partial, int nb
   }
 }
 
+// Statistics from the per-32-row-block (mean | M2) pairs the producing GEMM's epilogue wrote (hl_gemm2_bn_tf32x3): Chan's
+// parallel-variance merge in fp64.  Thread (ks, cl) merges the blocks ks, ks + 32, ... of column c0 + cl in ascending order,
+// then the 32 partial results are merged in ascending ks: a fixed order, reproducible.
+__global__ void bn_stats_final_tiles_kernel(const float* __restrict__ part, int32_t nrows_cap, const int32_t* __restrict__ nvalid,
+                                            int32_t width, float* __restrict__ stats, float* __restrict__ running_mean,
+                                            float* __restrict__ running_var, float momentum,
+                                            long long* __restrict__ batches_tracked) {
+  if (batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *batches_tracked += 1;
+  __shared__ double sh[3][32][kBnFinalCols];
+  const int32_t nrows = nvalid ? min(__ldg(nvalid), nrows_cap) : nrows_cap;
+  const int nblk = (nrows_cap + 31) / 32;
+  const int cl = threadIdx.x & (kBnFinalCols - 1), ks = threadIdx.x / kBnFinalCols;
+  const int c = blockIdx.x * kBnFinalCols + cl;
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  if (c < width)
+    for (int k = ks; k < nblk; k += 32) {
+      const int cnt = max(0, min(32, nrows - k * 32));
+      if (cnt == 0) break;                                            // blocks are ordered by row: nothing valid beyond
+      const double nb = (double)cnt, mb = (double)part[((int64_t)k * 2 + 0) * width + c], qb = (double)part[((int64_t)k * 2 + 1) * width + c];
+      const double tot = n + nb, delta = mb - mean;
+      mean += delta * nb / tot;
+      m2 += qb + delta * delta * n * nb / tot;
+      n = tot;
+    }
+  sh[0][ks][cl] = n; sh[1][ks][cl] = mean; sh[2][ks][cl] = m2;
+  __syncthreads();
+  if (ks != 0 || c >= width) return;
+  n = 0.0; mean = 0.0; m2 = 0.0;
+  for (int j = 0; j < 32; ++j) {
+    const double nb = sh[0][j][cl];
+    if (nb == 0.0) continue;
+    const double tot = n + nb, delta = sh[1][j][cl] - mean;
+    mean += delta * nb / tot;
+    m2 += sh[2][j][cl] + delta * delta * n * nb / tot;
+    n = tot;
+  }
+  if (n > 0.0) {
+    const float fm = (float)mean, var = (float)fmax(m2 / n, 0.0);
+    stats[c] = fm;
+    stats[width + c] = var;
+    if (running_mean) {
+      const float unbias = (float)(n / fmax(n - 1.0, 1.0));
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * fm;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * unbias;
+    }
+  } else {
+    stats[c] = 0.f;
+    stats[width + c] = 0.f;
+  }
+}
+
 // y = act(gamma (x - mean) rstd + beta): grid (row blocks of 128, column groups of 32 V), the mapping of BnMap
 template <int V>
 __global__ void __launch_bounds__(kBnThreads)
@@ -388,6 +439,30 @@ extern "C" int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_
                                                                     running_mean, running_mean ? running_var : nullptr, momentum,
                                                                     reinterpret_cast<long long*>(num_batches_tracked));
   HL_LAUNCH_CHECK("bn_stats_final_kernel");
+  if (V == 4) bn_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else if (V == 2) bn_apply_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else bn_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  HL_LAUNCH_CHECK("bn_apply_kernel");
+  return HL_OK;
+}
+
+// hl_bn_act_fwd with the statistics pass replaced by the block statistics the producing GEMM wrote (`bn_part`,
+// [ceil(nrows/32)][2][width]): finalize + apply, two launches instead of three and one pass over x less.
+extern "C" int hl_bn_act_fwd_tiles(const float* x, int64_t ld_x, int32_t nrows, int32_t width,
+                                   const float* gamma, const float* beta, float eps, float slope,
+                                   float* y, int64_t ld_y, float* stats, const int32_t* nvalid,
+                                   float* running_mean, float* running_var, float momentum,
+                                   int64_t* num_batches_tracked, const float* bn_part, hl_stream_t stream) {
+  using namespace hl;
+  if (nrows < 1 || width < 1 || !x || !y || !stats || !bn_part) return HL_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  bn_stats_final_tiles_kernel<<<(width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st>>>(
+      bn_part, nrows, nvalid, width, stats, running_mean, running_mean ? running_var : nullptr, momentum,
+      reinterpret_cast<long long*>(num_batches_tracked));
+  HL_LAUNCH_CHECK("bn_stats_final_tiles_kernel");
+  int V = vec_for(x, ld_x, width, 4);
+  V = min(V, vec_for(y, ld_y, width, V));
+  dim3 grid(bn_row_blocks(nrows), (width + 32 * V - 1) / (32 * V));
   if (V == 4) bn_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
   else if (V == 2) bn_apply_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
   else bn_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);

@@ -118,6 +118,44 @@ __device__ __forceinline__ uint64_t gm_desc_mnmajor_sw128(uint32_t smem_addr, ui
   return d;
 }
 
+// BatchNorm statistics of the output, from the epilogue (the Linear -> BatchNorm pairs of the path, lib/Hodge_Cheb_Conv.py:
+// 277-288, lib/Hodge_ST_Model.py:578-590): in the coalesced phase of the epilogue a lane holds 8 rows x 4 columns of the
+// FINAL values of a 32-row x 32-column block; the 4 lanes that share a column group combine over the block's valid rows
+// (two passes over registers: mean, then squared deviations -- no cancellation), and one of them writes mean and M2 of
+// the block.  bn_stats_final_tiles_kernel merges the blocks with Chan's formula in fp64, in a fixed order.
+__device__ __forceinline__ void gm_bn_block_stats(const float4 (&v)[8], int row_base, int sub_row, int nvalid_rows,
+                                                   float* __restrict__ part, int64_t block_index, int32_t N, int col, bool col_ok) {
+  const int cnt = max(0, min(32, nvalid_rows - row_base));               // valid rows of this 32-row block (warp-uniform)
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int it = 0; it < 8; ++it)
+    if (row_base + it * 4 + sub_row < nvalid_rows) { s[0] += v[it].x; s[1] += v[it].y; s[2] += v[it].z; s[3] += v[it].w; }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    s[k] += __shfl_xor_sync(0xffffffffu, s[k], 8);
+    s[k] += __shfl_xor_sync(0xffffffffu, s[k], 16);
+  }
+  const float inv = cnt > 0 ? 1.f / (float)cnt : 0.f;
+  const float m[4] = {s[0] * inv, s[1] * inv, s[2] * inv, s[3] * inv};
+  float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int it = 0; it < 8; ++it)
+    if (row_base + it * 4 + sub_row < nvalid_rows) {
+      const float d0 = v[it].x - m[0], d1 = v[it].y - m[1], d2 = v[it].z - m[2], d3 = v[it].w - m[3];
+      q[0] = fmaf(d0, d0, q[0]); q[1] = fmaf(d1, d1, q[1]); q[2] = fmaf(d2, d2, q[2]); q[3] = fmaf(d3, d3, q[3]);
+    }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    q[k] += __shfl_xor_sync(0xffffffffu, q[k], 8);
+    q[k] += __shfl_xor_sync(0xffffffffu, q[k], 16);
+  }
+  if (sub_row == 0 && col_ok) {
+    float* p = part + block_index * 2 * (int64_t)N + col;
+    *reinterpret_cast<float4*>(p) = make_float4(m[0], m[1], m[2], m[3]);
+    *reinterpret_cast<float4*>(p + N) = make_float4(q[0], q[1], q[2], q[3]);
+  }
+}
+
 struct GemmParams {
   int32_t M, N, K, bn, stages, tmem_cols;
   const float* bias;
@@ -133,6 +171,8 @@ struct GemmParams {
   int32_t num_tiles, tiles_n;   // persistent kernel: output tiles in total / along N
   int32_t acc_stride;           // persistent kernel: TMEM columns between the two accumulators
   int32_t x_tiles_each;         // wgrad with TWO X operands (map_bhi, map_blo): column tiles per operand (0 = one operand)
+  float* bn_part;               // forward: per 32-row block BatchNorm statistics of the output [ceil(M/32)][2][N] (mean | M2), or NULL
+  const int32_t* bn_nvalid;     // device row count the statistics cover (rows beyond are padding), or NULL = M
 };
 
 // MODE 0: C = A[M,K] B[N,K]^T, both K-major, B pre-split (map_b = hi, map_b2 = lo).
@@ -426,6 +466,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               num_kb > 0 ? make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]))
                          : make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
+        float4 fin[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int lr = it * 4 + sub_row;
@@ -434,6 +475,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
           if (P.accumulate) { v.x += old[it].x; v.y += old[it].y; v.z += old[it].z; v.w += old[it].w; }
           if (col_ok && rr < P.M) *reinterpret_cast<float4*>(Cbase + (int64_t)rr * P.ldc + c_off + col) = v;
+          fin[it] = v;
+        }
+        if (MODE == 0 && P.bn_part && m0 + quad * 32 < P.M) {             // (warp-uniform) blocks past the last row do not exist
+          const int nvr = P.bn_nvalid ? min(__ldg(P.bn_nvalid), P.M) : P.M;
+          gm_bn_block_stats(fin, m0 + quad * 32, sub_row, nvr, P.bn_part, (int64_t)(m0 / 32 + quad), P.N, col, col_ok);
         }
         __syncwarp();                                                 // the staging tile is reused by the next chunk
         continue;
@@ -648,6 +694,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
             *reinterpret_cast<float4*>(mine + j) =
                 make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
           __syncwarp();
+          float4 fin[8];
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8) {
             const int lr = i8 * 4 + sub_row;
@@ -656,6 +703,11 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
             v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
             if (P.accumulate) { v.x += old[i8].x; v.y += old[i8].y; v.z += old[i8].z; v.w += old[i8].w; }
             if (col_ok && rr < P.M) *reinterpret_cast<float4*>(P.C + (int64_t)rr * P.ldc + col) = v;
+            fin[i8] = v;
+          }
+          if (P.bn_part && m0 + quad * 32 < P.M) {
+            const int nvr = P.bn_nvalid ? min(__ldg(P.bn_nvalid), P.M) : P.M;
+            gm_bn_block_stats(fin, m0 + quad * 32, sub_row, nvr, P.bn_part, (int64_t)(m0 / 32 + quad), P.N, col, col_ok);
           }
           __syncwarp();
           continue;
@@ -772,21 +824,37 @@ extern "C" int hl_tf32_split_batch(const hl_split_desc* table, int32_t n_entries
   return HL_OK;
 }
 
-extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const float* A2, int64_t lda2, int32_t K2,
-                               const float* Bhi, const float* Blo, int64_t ldb, int32_t M, int32_t N,
-                               const float* bias, float* C, int64_t ldc, int accumulate, hl_stream_t stream);
+extern "C" int hl_gemm2_bn_tf32x3(const float* A, int64_t lda, int32_t K, const float* A2, int64_t lda2, int32_t K2,
+                                  const float* Bhi, const float* Blo, int64_t ldb, int32_t M, int32_t N,
+                                  const float* bias, float* C, int64_t ldc, int accumulate, float* bn_part,
+                                  const int32_t* bn_nvalid, hl_stream_t stream);
 
 // returns HL_OK, or 1 when the shape / alignment is not supported (caller uses a library GEMM instead)
 extern "C" int hl_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb,
                               int32_t M, int32_t N, int32_t K, const float* bias, float* C, int64_t ldc,
                               int accumulate, hl_stream_t stream) {
-  return hl_gemm2_tf32x3(A, lda, K, nullptr, 0, 0, Bhi, Blo, ldb, M, N, bias, C, ldc, accumulate, stream);
+  return hl_gemm2_bn_tf32x3(A, lda, K, nullptr, 0, 0, Bhi, Blo, ldb, M, N, bias, C, ldc, accumulate, nullptr, nullptr, stream);
 }
 
-// C = [A1 | A2] * B^T: B = [N, pad32(K1) + K2] (the columns of the second block start at pad32(K1)).
 extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const float* A2, int64_t lda2, int32_t K2,
                                const float* Bhi, const float* Blo, int64_t ldb, int32_t M, int32_t N,
                                const float* bias, float* C, int64_t ldc, int accumulate, hl_stream_t stream) {
+  return hl_gemm2_bn_tf32x3(A, lda, K, A2, lda2, K2, Bhi, Blo, ldb, M, N, bias, C, ldc, accumulate, nullptr, nullptr, stream);
+}
+
+extern "C" size_t hl_gemm_bn_part_floats(int32_t M, int32_t N) {
+  if (M < 0 || N < 0) return 0;
+  return (size_t)((M + 31) / 32) * 2 * (size_t)N;
+}
+
+// C = [A1 | A2] * B^T: B = [N, pad32(K1) + K2] (the columns of the second block start at pad32(K1)).
+// bn_part (nullable, [ceil(M/32)][2][N] floats): BatchNorm statistics of the FINAL output values per 32-row block (mean | M2
+// over the rows below *bn_nvalid), written by the epilogue -- pass it on the last launch that touches C; needs 16-byte aligned
+// C rows (returns 1 otherwise, like every unsupported shape).
+extern "C" int hl_gemm2_bn_tf32x3(const float* A, int64_t lda, int32_t K, const float* A2, int64_t lda2, int32_t K2,
+                                  const float* Bhi, const float* Blo, int64_t ldb, int32_t M, int32_t N,
+                                  const float* bias, float* C, int64_t ldc, int accumulate, float* bn_part,
+                                  const int32_t* bn_nvalid, hl_stream_t stream) {
   using namespace hl;
   if (M < 0 || N < 1 || K < 1 || K2 < 0 || !C) return HL_ERR_INVALID;
   if (M == 0) return HL_OK;
@@ -797,6 +865,7 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
   // TMA: 16-byte aligned base and row pitch; MMA: N multiple of 16, one N tile of <= 256 columns per CTA
   if (lda % 4 != 0 || ldb % 4 != 0 || !aligned_to(A, 16) || !aligned_to(Bhi, 16) || !aligned_to(Blo, 16)) return 1;
   if (N % 16 != 0) return 1;
+  if (bn_part && (ldc % 4 != 0 || !aligned_to(C, 16) || !aligned_to(bn_part, 16))) return 1;
   // Column tile: as wide as possible (<= 256 columns, multiple of 16; TMA zero-fills the overhang).  Narrower
   // tiles with two co-resident CTAs per SM were measured slower (A re-read from L2, N=64 MMAs): 181 vs 155 us
   // on [24000,1408]x[1408,256].
@@ -879,7 +948,7 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
       Q.bias = bias; Q.C = C; Q.ldc = ldc; Q.accumulate = accumulate; Q.k_per_split = 0; Q.split_stride = 0;
       Q.tmem_a_col = 2 * acc_stride; Q.colsum_ws = nullptr; Q.conv_groups = 1;
       Q.kb_first = K2 > 0 ? kb_first : 0x7fffffff;
-      Q.x_tiles_each = 0;
+      Q.x_tiles_each = 0; Q.bn_part = bn_part; Q.bn_nvalid = bn_nvalid;
       Q.tiles_n = ntiles; Q.num_tiles = ((M + kGmBM - 1) / kGmBM) * ntiles; Q.acc_stride = acc_stride;
       const int sms = device_sm_count();
       const int grid_ps = Q.num_tiles < sms ? Q.num_tiles : sms;
@@ -890,7 +959,7 @@ extern "C" int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const flo
   }
   GemmParams P;
   P.M = M; P.N = N; P.K = Ktot; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
-  P.num_tiles = 0; P.tiles_n = 1; P.acc_stride = 0; P.x_tiles_each = 0;
+  P.num_tiles = 0; P.tiles_n = 1; P.acc_stride = 0; P.x_tiles_each = 0; P.bn_part = bn_part; P.bn_nvalid = bn_nvalid;
   P.bias = bias; P.C = C; P.ldc = ldc; P.accumulate = accumulate; P.k_per_split = 0; P.split_stride = 0;
   P.tmem_a_col = tmem_a_col; P.colsum_ws = nullptr; P.conv_groups = 1;
   P.kb_first = K2 > 0 ? kb_first : 0x7fffffff;
@@ -1079,7 +1148,7 @@ static int wgrad_launch(const float* g, int64_t ld_g, const float* x, int64_t ld
     HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   GemmParams P;
-  P.num_tiles = 0; P.tiles_n = 1; P.acc_stride = 0; P.x_tiles_each = x2 ? ntiles : 0;
+  P.num_tiles = 0; P.tiles_n = 1; P.acc_stride = 0; P.x_tiles_each = x2 ? ntiles : 0; P.bn_part = nullptr; P.bn_nvalid = nullptr;
   P.M = fo; P.N = fi; P.K = nrows; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
   P.bias = nullptr; P.C = reinterpret_cast<float*>(workspace); P.ldc = fi_tot; P.accumulate = 0;
   P.k_per_split = k_per_split; P.split_stride = (int64_t)fo * fi_tot; P.tmem_a_col = tmem_a_col;

@@ -247,7 +247,7 @@ class _StackLinear(torch.autograd.Function):
     def forward(ctx, stack, side, d, weight, bias, *deps):
         N.require_cuda_f32(weight, bias)
         xa, xb = stack.view("tr", side, 0, d), stack.view("own", side, 0, d)
-        y = F_hl.dense2(xa, weight[:, :d], xb, weight[:, d:], bias)
+        y = F_hl.dense2(xa, weight[:, :d], xb, weight[:, d:], bias, bn=F_hl._take_bn_request())
         for kind in ("tr", "own"):
             stack.consumed[(kind, side)] = max(stack.consumed[(kind, side)], d)
         ctx.stack, ctx.side, ctx.d, ctx.has_bias, ctx.ndeps = stack, side, d, bias is not None, len(deps)

@@ -242,9 +242,60 @@ def _view_key(t):
     return (t.data_ptr(), tuple(t.shape), tuple(t.stride()))
 
 
-def dense(a, w, bias=None, out=None, accumulate=False, transpose_w=False):
+class BnTiles:
+    """Request for the BatchNorm statistics of a Linear / polynomial-conv output from the GEMM epilogue
+    (hl_gemm2_bn_tf32x3): `with bn_stats_from_epilogue(nvalid) as req: h = linear(...)`, then `bn_act_train(h, ..., tiles=req)`.
+    The launch that writes the FINAL values of the output fills `part` ([ceil(M/32)][2][N]: mean | M2 of every 32-row
+    block over the rows below *nvalid) and `key`; when it could not (cuBLAS path, an odd shape) `part` stays None and
+    the BatchNorm runs its own statistics pass as before."""
+    __slots__ = ("nvalid", "part", "key", "out")
+
+    def __init__(self, nvalid):
+        self.nvalid, self.part, self.key, self.out = nvalid, None, None, None
+
+    def matches(self, x, nvalid):
+        return self.part is not None and self.key == (x.data_ptr(), x.shape[0], x.shape[1], x.stride(0)) \
+            and N.ptr(self.nvalid) == N.ptr(nvalid)
+
+
+_BN_EPILOGUE = _os.environ.get("HL_BN_EPILOGUE", "1") != "0"
+_BN_REQ = [None]
+
+
+class bn_stats_from_epilogue:
+    def __init__(self, nvalid=None, enabled=True):
+        self.req = BnTiles(nvalid) if (enabled and _BN_EPILOGUE) else None
+
+    def __enter__(self):
+        self.prev, _BN_REQ[0] = _BN_REQ[0], self.req
+        return self.req
+
+    def __exit__(self, *a):
+        _BN_REQ[0] = self.prev
+
+
+def _take_bn_request():
+    """The pending request (at most one producer serves it: the first autograd Function whose forward runs inside the
+    `with`)."""
+    req, _BN_REQ[0] = _BN_REQ[0], None
+    return req
+
+
+def _bn_part_for(bn, M, n_out, device):
+    if bn is None or M < 1:
+        return None
+    return torch.empty(N.lib().hl_gemm_bn_part_floats(M, n_out), dtype=torch.float32, device=device)
+
+
+def _bn_done(bn, part, out):
+    # `out` is held so that its address cannot be handed to another tensor of the same shape while the request lives
+    bn.part, bn.key, bn.out = part, (out.data_ptr(), out.shape[0], out.shape[1], out.stride(0)), out
+
+
+def dense(a, w, bias=None, out=None, accumulate=False, transpose_w=False, bn=None):
     """out (=|+=) a @ w.T (+ bias)   [transpose_w: a @ w].  fp32-accurate tcgen05 GEMM (3xTF32 split) when the
-    shape allows (N % 16 == 0, 16-byte aligned rows), else the cuBLAS fp32 GEMM."""
+    shape allows (N % 16 == 0, 16-byte aligned rows), else the cuBLAS fp32 GEMM.  `bn` (BnTiles): also the
+    BatchNorm block statistics of the result from the epilogue."""
     L = N.lib()
     M, K = a.shape
     n_out = w.shape[1] if transpose_w else w.shape[0]
@@ -259,9 +310,17 @@ def dense(a, w, bias=None, out=None, accumulate=False, transpose_w=False):
         tr = 1 if transpose_w else 0
         hi, lo = _split_weights(("1", tr) + _view_key(w), (w,), (n_out, kp),
                                 [lambda h, l: (w.data_ptr(), w.stride(0), rows, cols, tr, h.data_ptr(), l.data_ptr(), kp)], False)
-        rc = L.hl_gemm_tf32x3(a.data_ptr(), a.stride(0), hi.data_ptr(), lo.data_ptr(), kp, M, n_out, K, N.ptr(bias),
-                              out.data_ptr(), out.stride(0), 1 if accumulate else 0, N.stream_ptr())
+        part = _bn_part_for(bn, M, n_out, a.device)
+        if part is None:
+            rc = L.hl_gemm_tf32x3(a.data_ptr(), a.stride(0), hi.data_ptr(), lo.data_ptr(), kp, M, n_out, K, N.ptr(bias),
+                                  out.data_ptr(), out.stride(0), 1 if accumulate else 0, N.stream_ptr())
+        else:
+            rc = L.hl_gemm2_bn_tf32x3(a.data_ptr(), a.stride(0), K, None, 0, 0, hi.data_ptr(), lo.data_ptr(), kp, M, n_out,
+                                      N.ptr(bias), out.data_ptr(), out.stride(0), 1 if accumulate else 0, part.data_ptr(),
+                                      N.ptr(bn.nvalid), N.stream_ptr())
         if rc == 0:
+            if part is not None:
+                _bn_done(bn, part, out)
             return out
         if rc != 1:
             N.check(rc, "hl_gemm_tf32x3")
@@ -277,7 +336,7 @@ def dense(a, w, bias=None, out=None, accumulate=False, transpose_w=False):
     return out
 
 
-def dense2(a1, w1, a2, w2, bias=None, out=None, accumulate=False):
+def dense2(a1, w1, a2, w2, bias=None, out=None, accumulate=False, bn=None):
     """out (=|+=) a1 @ w1.T + a2 @ w2.T (+ bias) in ONE tensor-core launch (the sum stays in TMEM)."""
     L = N.lib()
     M, k1 = a1.shape
@@ -297,14 +356,18 @@ def dense2(a1, w1, a2, w2, bias=None, out=None, accumulate=False):
         if out is None:
             out = torch.empty((M, n_out), dtype=torch.float32, device=a1.device)
             accumulate = False
-        rc = L.hl_gemm2_tf32x3(a1.data_ptr(), a1.stride(0), k1, a2.data_ptr(), a2.stride(0), k2, hi.data_ptr(), lo.data_ptr(), kt,
-                               M, n_out, N.ptr(bias), out.data_ptr(), out.stride(0), 1 if accumulate else 0, st)
+        part = _bn_part_for(bn, M, n_out, a1.device)
+        rc = L.hl_gemm2_bn_tf32x3(a1.data_ptr(), a1.stride(0), k1, a2.data_ptr(), a2.stride(0), k2, hi.data_ptr(), lo.data_ptr(), kt,
+                                  M, n_out, N.ptr(bias), out.data_ptr(), out.stride(0), 1 if accumulate else 0, N.ptr(part),
+                                  N.ptr(bn.nvalid) if part is not None else None, st)
         if rc == 0:
+            if part is not None:
+                _bn_done(bn, part, out)
             return out
         if rc != 1:
-            N.check(rc, "hl_gemm2_tf32x3")
+            N.check(rc, "hl_gemm2_bn_tf32x3")
     out = dense(a1, w1, bias, out=out, accumulate=accumulate)
-    return dense(a2, w2, None, out=out, accumulate=True)
+    return dense(a2, w2, None, out=out, accumulate=True, bn=bn)
 
 
 def wgrad(g, x, out=None, accumulate=False, bias_out=None, bias_accumulate=False):
@@ -404,11 +467,12 @@ class _Linear(torch.autograd.Function):
         N.require_cuda_f32(xa, xb, weight, bias)
         d = xa.shape[1]
         xa = xa.contiguous() if xa.stride(1) != 1 else xa
+        bn = _take_bn_request()
         if xb is None:
-            y = dense(xa, weight, bias)
+            y = dense(xa, weight, bias, bn=bn)
         else:
             xb = xb.contiguous() if xb.stride(1) != 1 else xb
-            y = dense2(xa, weight[:, :d], xb, weight[:, d:], bias)
+            y = dense2(xa, weight[:, :d], xb, weight[:, d:], bias, bn=bn)
         ctx.save_for_backward(xa, xb, weight)
         ctx.has_bias = bias is not None
         ctx.params = (weight, bias)                 # the Parameter objects (for fused gradient accumulation)
@@ -545,15 +609,20 @@ class _PolyConv(torch.autograd.Function):
         R, width = x.shape
         (t,) = poly_basis_fwd(family, K, [op], [x], width)
         xv = x.view(-1, inner)
+        bn = _take_bn_request()
+        if inner != width:                          # [R, T, C] input: the BatchNorm rows are not the GEMM rows
+            bn = None
         if K == 1:
-            out = dense(xv, weights[0], bias)
+            out = dense(xv, weights[0], bias, bn=bn)
         else:
-            out = dense2(xv, weights[0], t[0].view(-1, inner), weights[1], bias)
+            out = dense2(xv, weights[0], t[0].view(-1, inner), weights[1], bias, bn=bn if K == 2 else None)
             for k in range(2, K, 2):
+                last = bn if k + 2 >= K else None   # statistics of the FINAL values: the launch that completes the sum
                 if k + 1 < K:
-                    dense2(t[k - 1].view(-1, inner), weights[k], t[k].view(-1, inner), weights[k + 1], None, out=out, accumulate=True)
+                    dense2(t[k - 1].view(-1, inner), weights[k], t[k].view(-1, inner), weights[k + 1], None, out=out, accumulate=True,
+                           bn=last)
                 else:
-                    dense(t[k - 1].view(-1, inner), weights[k], None, out=out, accumulate=True)
+                    dense(t[k - 1].view(-1, inner), weights[k], None, out=out, accumulate=True, bn=last)
         ctx.op, ctx.family, ctx.inner, ctx.has_bias = op, family, inner, bias is not None
         ctx.params = (bias, weights)
         ctx.save_for_backward(x, t, *weights)
@@ -863,9 +932,11 @@ def segment_mean(src, seg, scale=None):
 # ---------------------------------------------------------------------------------------------
 class _BnAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, slope, nvalid, running_mean, running_var, momentum, counter=None, tap=None):
+    def forward(ctx, x, gamma, beta, eps, slope, nvalid, running_mean, running_var, momentum, counter=None, tap=None,
+                tiles=None):
         N.require_cuda_f32(x, gamma, beta)
         L = N.lib()
+        from_tiles = tiles is not None and tiles.matches(x, nvalid)
         x, ldx = N.row_major(x)
         R, F = x.shape
         # tap = (stack, side, c0, c1): the output is block [c0, c1) of a dense-connection buffer (dense_stack.DenseStack),
@@ -880,12 +951,18 @@ class _BnAct(torch.autograd.Function):
             ctx.set_materialize_grads(False)
             return y, stats
         ctx.empty = False
-        nb = L.hl_bn_workspace(R, F)
-        ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
-        N.check(L.hl_bn_act_fwd(x.data_ptr(), ldx, R, F, N.ptr(gamma), N.ptr(beta), eps, slope,
-                                y.data_ptr(), y.stride(0), stats.data_ptr(), N.ptr(nvalid), N.ptr(running_mean),
-                                N.ptr(running_var), float(momentum), N.ptr(counter), ws.data_ptr(), nb, N.stream_ptr()),
-                "hl_bn_act_fwd")
+        if from_tiles:                              # statistics already reduced per 32-row block by the producing GEMM
+            N.check(L.hl_bn_act_fwd_tiles(x.data_ptr(), ldx, R, F, N.ptr(gamma), N.ptr(beta), eps, slope,
+                                          y.data_ptr(), y.stride(0), stats.data_ptr(), N.ptr(nvalid), N.ptr(running_mean),
+                                          N.ptr(running_var), float(momentum), N.ptr(counter), tiles.part.data_ptr(),
+                                          N.stream_ptr()), "hl_bn_act_fwd_tiles")
+        else:
+            nb = L.hl_bn_workspace(R, F)
+            ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+            N.check(L.hl_bn_act_fwd(x.data_ptr(), ldx, R, F, N.ptr(gamma), N.ptr(beta), eps, slope,
+                                    y.data_ptr(), y.stride(0), stats.data_ptr(), N.ptr(nvalid), N.ptr(running_mean),
+                                    N.ptr(running_var), float(momentum), N.ptr(counter), ws.data_ptr(), nb, N.stream_ptr()),
+                    "hl_bn_act_fwd")
         ctx.eps, ctx.slope, ctx.nvalid = eps, slope, nvalid
         ctx.params = (gamma, beta)
         ctx.save_for_backward(x, y, gamma, stats)
@@ -899,9 +976,9 @@ class _BnAct(torch.autograd.Function):
         if ctx.tap is not None:                     # stack-accumulated gradient + autograd's piece: summed inside the kernels
             dy, dy2 = ctx.tap[0].collect("own", *ctx.tap[1:], dy, fuse=True)
         if dy is None:
-            return (None,) * 11
+            return (None,) * 12
         if ctx.empty:
-            return (torch.zeros_like(dy),) + (None,) * 10
+            return (torch.zeros_like(dy),) + (None,) * 11
         x, y, gamma, stats = ctx.saved_tensors
         L = N.lib()
         R, F = x.shape
@@ -924,7 +1001,7 @@ class _BnAct(torch.autograd.Function):
             dgamma = None
         if fused or ctx.params[1] is None:
             dbeta = None
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
 class _BnActEval(torch.autograd.Function):
@@ -1058,9 +1135,10 @@ def bn_act_train_synced(x, gamma, beta, group, eps=1e-5, slope=0.0, nvalid=None,
 
 
 def bn_act_train(x, gamma, beta, eps=1e-5, slope=0.0, nvalid=None, running_mean=None, running_var=None, momentum=0.1,
-                 counter=None, tap=None):
+                 counter=None, tap=None, tiles=None):
     """Training-mode BatchNorm1d over rows + (leaky) ReLU; returns (y, stats[2F] = mean | biased var).
     `nvalid`: optional device int32 scalar -- rows beyond it are padding (excluded, written as zeros).
     running_mean / running_var (optional) are updated in the same launch, like nn.BatchNorm1d; `counter`
-    (optional int64 scalar: num_batches_tracked) is incremented there too."""
-    return _BnAct.apply(x, gamma, beta, float(eps), float(slope), nvalid, running_mean, running_var, momentum, counter, tap)
+    (optional int64 scalar: num_batches_tracked) is incremented there too.  `tiles` (BnTiles, optional): block statistics
+    of x left by the GEMM that produced it (bn_stats_from_epilogue) -- the statistics pass over x is skipped."""
+    return _BnAct.apply(x, gamma, beta, float(eps), float(slope), nvalid, running_mean, running_var, momentum, counter, tap, tiles)

@@ -270,10 +270,12 @@ MSI = NodeEdgeInt
 def _mlp_stack(seq, stack, side, d, nvalid=None):
     """`_mlp` reading [transferred | own] in place from the dense-connection buffers of `stack`."""
     lin0, bn0, _, lin1, bn1, _ = seq
-    h = _ds.stack_linear(stack, side, d, lin0.weight, lin0.bias)
-    h = _bn_relu(bn0, h, 0.0, nvalid)
-    h = F_hl.linear(h, lin1.weight, lin1.bias)
-    return _bn_relu(bn1, h, 0.0, nvalid)
+    with _epilogue_stats(bn0, nvalid) as tiles:
+        h = _ds.stack_linear(stack, side, d, lin0.weight, lin0.bias)
+    h = _bn_relu(bn0, h, 0.0, nvalid, tiles=tiles)
+    with _epilogue_stats(bn1, nvalid) as tiles:
+        h = F_hl.linear(h, lin1.weight, lin1.bias)
+    return _bn_relu(bn1, h, 0.0, nvalid, tiles=tiles)
 
 
 def node_edge_int_on_stack(module, stack, nvalid=(None, None)):
@@ -301,11 +303,22 @@ def _into(tap, y):
     return y if tap is None else _ds._Publish.apply(y, *tap)
 
 
-def _bn_relu(bn, x, slope=0.0, nvalid=None, tap=None):
+def _epilogue_stats(bn, nvalid=None):
+    """`with _epilogue_stats(bn, nvalid) as tiles: h = <Linear / conv>` then `_bn_relu(bn, h, ..., tiles=tiles)`: the
+    Linear -> BatchNorm1d pairs of the reference (lib/Hodge_Cheb_Conv.py:277-288, lib/Hodge_ST_Model.py:578-601) with
+    the batch statistics reduced per 32-row block in the GEMM epilogue instead of by a separate pass over h.  Only for
+    the plain training-mode BatchNorm (not eval(), not the synced variant: those do not read batch statistics of h)."""
+    if isinstance(bn, GraphBatchNorm):
+        bn = bn.module
+    on = (bn.training or not bn.track_running_stats) and _parallel.sync_batchnorm_group() is False
+    return F_hl.bn_stats_from_epilogue(nvalid, enabled=on)
+
+
+def _bn_relu(bn, x, slope=0.0, nvalid=None, tap=None, tiles=None):
     """nn.BatchNorm1d (+ReLU) through the fused kernels in training mode; running statistics updated
     exactly like torch (momentum, unbiased variance).  `nvalid` (device int32 scalar) marks the rows
     beyond it as padding of a fixed-capacity batch.  `tap` = (stack, side, c0, c1): the output is written
-    straight into that block of a dense-connection buffer (dense_stack.DenseStack)."""
+    straight into that block of a dense-connection buffer (dense_stack.DenseStack).  `tiles`: see _epilogue_stats."""
     if not (bn.training or not bn.track_running_stats):      # eval(): the running statistics, same apply kernel
         return _into(tap, F_hl.bn_act_eval(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, slope, nvalid))
     track = bn.track_running_stats and bn.training
@@ -325,7 +338,7 @@ def _bn_relu(bn, x, slope=0.0, nvalid=None, tap=None):
     if group is not False:                    # opt-in: statistics over all data-parallel ranks (parallel.enable_sync_batchnorm)
         y, _ = F_hl.bn_act_train_synced(x, bn.weight, bn.bias, group, bn.eps, slope, nvalid, rm, rv, m, counter)
         return _into(tap, y)
-    y, _ = F_hl.bn_act_train(x, bn.weight, bn.bias, bn.eps, slope, nvalid, rm, rv, m, counter, tap)
+    y, _ = F_hl.bn_act_train(x, bn.weight, bn.bias, bn.eps, slope, nvalid, rm, rv, m, counter, tap, tiles)
     return y
 
 
@@ -342,10 +355,17 @@ def _mlp(seq, other, transfer, own, nvalid=None):
         t = transfer(F_hl.linear_part(other, lin0.weight, 0, d))
         h = F_hl.linear_part(own, lin0.weight, d, lin0.weight.shape[1], lin0.bias, addend=t)
     else:
-        h = F_hl.linear(transfer(other), lin0.weight, lin0.bias, x2=own)
+        t = transfer(other)
+        with _epilogue_stats(bn0, nvalid) as tiles:
+            h = F_hl.linear(t, lin0.weight, lin0.bias, x2=own)
+        h = _bn_relu(bn0, h, 0.0, nvalid, tiles=tiles)
+        with _epilogue_stats(bn1, nvalid) as tiles:
+            h = F_hl.linear(h, lin1.weight, lin1.bias)
+        return _bn_relu(bn1, h, 0.0, nvalid, tiles=tiles)
     h = _bn_relu(bn0, h, 0.0, nvalid)
-    h = F_hl.linear(h, lin1.weight, lin1.bias)
-    return _bn_relu(bn1, h, 0.0, nvalid)
+    with _epilogue_stats(bn1, nvalid) as tiles:
+        h = F_hl.linear(h, lin1.weight, lin1.bias)
+    return _bn_relu(bn1, h, 0.0, nvalid, tiles=tiles)
 
 
 class GraphBatchNorm(nn.Module):
@@ -359,8 +379,8 @@ class GraphBatchNorm(nn.Module):
     def forward(self, x):
         return _bn_relu(self.module, x, slope=1.0)
 
-    def forward_act(self, x, slope=0.0, nvalid=None, tap=None):
-        return _bn_relu(self.module, x, slope, nvalid, tap)
+    def forward_act(self, x, slope=0.0, nvalid=None, tap=None, tiles=None):
+        return _bn_relu(self.module, x, slope, nvalid, tap, tiles)
 
 
 class NEConv(nn.Module):
@@ -386,15 +406,17 @@ class NEConv(nn.Module):
         if stack is not None and not cat:
             c0, c1 = stack.reserve(self.module_1.module.num_features)
             taps = ((stack, "t", c0, c1), (stack, "s", c0, c1))
-        x_t = self.module_1.forward_act(self.module_0(x_t, edge_index_t, edge_weight_t), self.slope, nvalid[0],
-                                        None if drop else taps[0])
+        with _epilogue_stats(self.module_1, nvalid[0]) as tiles:
+            h_t = self.module_0(x_t, edge_index_t, edge_weight_t)
+        x_t = self.module_1.forward_act(h_t, self.slope, nvalid[0], None if drop else taps[0], tiles)
         if self.p > 0.0:
             x_t = torch.nn.functional.dropout(x_t, self.p, self.training)
             if drop:
                 x_t = _into(taps[0], x_t)
         with (ln.edge_ctx() if ln is not None else contextlib.nullcontext()):   # x_s lives on the edge lane (lanes.py)
-            x_s = self.module_5.forward_act(self.module_4(x_s, edge_index_s, edge_weight_s), self.slope, nvalid[1],
-                                            None if drop else taps[1])
+            with _epilogue_stats(self.module_5, nvalid[1]) as tiles:
+                h_s = self.module_4(x_s, edge_index_s, edge_weight_s)
+            x_s = self.module_5.forward_act(h_s, self.slope, nvalid[1], None if drop else taps[1], tiles)
             if self.p > 0.0:
                 x_s = torch.nn.functional.dropout(x_s, self.p, self.training)
                 if drop:

@@ -10,7 +10,7 @@ from .. import functional as F_hl
 from .. import lanes as _lanes
 from ..dense_stack import new_stack
 from ..simplex import Hodge1Factor, incidence_for, operator_for
-from .Hodge_Cheb_Conv import NEConv, NodeEdgeInt, adj2par1, degree, _bn_relu, node_edge_int_on_stack
+from .Hodge_Cheb_Conv import NEConv, NodeEdgeInt, adj2par1, degree, _bn_relu, _epilogue_stats, node_edge_int_on_stack
 
 
 def _share_tables(ln, op_s, inc):
@@ -34,7 +34,9 @@ class _MlpBlock(nn.Sequential):
 
     def forward(self, x, nvalid=None):
         lin, bn, _, drop = self
-        return drop(_bn_relu(bn, F_hl.linear(x, lin.weight, lin.bias), 0.0, nvalid))
+        with _epilogue_stats(bn, nvalid) as tiles:
+            h = F_hl.linear(x, lin.weight, lin.bias)
+        return drop(_bn_relu(bn, h, 0.0, nvalid, tiles=tiles))
 
 
 class HL_HGCNN_zinc_dense_int3_pyr(nn.Module):

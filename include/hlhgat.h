@@ -251,6 +251,14 @@ int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_t width,
                   float* running_mean /* nullable */, float* running_var, float momentum,
                   int64_t* num_batches_tracked /* device, nullable: incremented by one in the same launch */,
                   void* workspace, size_t workspace_bytes, hl_stream_t stream);
+/* hl_bn_act_fwd without its statistics pass: `bn_part` ([ceil(nrows/32)][2][width]: mean | M2 of every 32-row block) was
+ * written by the epilogue of the GEMM that produced x (hl_gemm2_bn_tf32x3, the Linear -> BatchNorm pairs of
+ * lib/Hodge_Cheb_Conv.py:277-288 and lib/Hodge_ST_Model.py:578-590); merged with Chan's formula in fp64, then applied. */
+int hl_bn_act_fwd_tiles(const float* x, int64_t ld_x, int32_t nrows, int32_t width,
+                        const float* gamma, const float* beta, float eps, float slope,
+                        float* y, int64_t ld_y, float* stats, const int32_t* nvalid,
+                        float* running_mean, float* running_var, float momentum,
+                        int64_t* num_batches_tracked, const float* bn_part, hl_stream_t stream);
 int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64_t ld_y,
                   const float* dy, int64_t ld_dy, const float* dy2 /* nullable: a second gradient piece, added on the fly */, int64_t ld_dy2,
                   int32_t nrows, int32_t width,
@@ -361,6 +369,13 @@ int hl_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float* B
 int hl_gemm2_tf32x3(const float* A, int64_t lda, int32_t K, const float* A2, int64_t lda2, int32_t K2,
                     const float* Bhi, const float* Blo, int64_t ldb, int32_t M, int32_t N,
                     const float* bias, float* C, int64_t ldc, int accumulate, hl_stream_t stream);
+/* ... with the BatchNorm statistics of the FINAL output values from the epilogue: bn_part [hl_gemm_bn_part_floats(M, N)] gets
+ * (mean | M2) of every 32-row block over the rows below *bn_nvalid (NULL = M); pass it on the last launch that touches C. */
+size_t hl_gemm_bn_part_floats(int32_t M, int32_t N);
+int hl_gemm2_bn_tf32x3(const float* A, int64_t lda, int32_t K, const float* A2, int64_t lda2, int32_t K2,
+                       const float* Bhi, const float* Blo, int64_t ldb, int32_t M, int32_t N,
+                       const float* bias, float* C, int64_t ldc, int accumulate, float* bn_part /* nullable */,
+                       const int32_t* bn_nvalid /* nullable */, hl_stream_t stream);
 /* Weight gradient on the same tensor-core path: dw[fo,fi] (=|+=) g[R,fo]^T x[R,fi].  Both operands are
  * consumed MN-major straight from their row-major storage ({32 x 32} TMA boxes, no transposes), split into
  * hi/lo inside the kernel, the R rows are divided over CTAs and the partial tiles are summed in a fixed

@@ -495,3 +495,107 @@ def test_wgrad2_two_operands_one_launch(R, fo, fi):
     F_hl.wgrad2(g, x1, x2, acc1, acc2, accumulate=True, bias_out=accb, bias_accumulate=True)
     assert float((acc1.double() - want1).abs().max()) < 1e-4 * scale and float((acc2.double() - want2).abs().max()) < 1e-4 * scale
     assert float((accb.double() - wantb).abs().max()) < 1e-5 * float(rb.abs().max())
+
+
+# ------------------------------------------------------------------------------------------
+# BatchNorm statistics from the GEMM epilogue (hl_gemm2_bn_tf32x3 + hl_bn_act_fwd_tiles)
+def _merge_tiles(part, M, Nn, nvalid):
+    """Chan merge of the per-32-row-block (mean | M2) pairs on the host in fp64 -> mean, biased variance."""
+    nv = M if nvalid is None else min(int(nvalid), M)
+    p = part.view(-1, 2, Nn).double().cpu()
+    n, mean, m2 = 0.0, torch.zeros(Nn, dtype=torch.float64), torch.zeros(Nn, dtype=torch.float64)
+    for k in range(p.shape[0]):
+        cnt = max(0, min(32, nv - 32 * k))
+        if cnt == 0:
+            break
+        d = p[k, 0] - mean
+        tot = n + cnt
+        mean = mean + d * cnt / tot
+        m2 = m2 + p[k, 1] + d * d * n * cnt / tot
+        n = tot
+    return mean, m2 / max(n, 1.0)
+
+
+@pytest.mark.parametrize("M,Nn,K,K2", [(300, 64, 64, 0), (24001, 256, 192, 64), (60, 64, 32, 0), (77000, 64, 128, 128),
+                                       (5000, 128, 28, 0), (40000, 48, 64, 64), (1, 64, 64, 0), (129, 256, 704, 0)])
+@pytest.mark.parametrize("nvalid", [None, 0.63])
+def test_gemm_epilogue_block_statistics(M, Nn, K, K2, nvalid):
+    g = torch.Generator().manual_seed(M + Nn)
+    a1 = torch.randn(M, K, generator=g).to(DEV)
+    w1 = (torch.randn(Nn, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(Nn, generator=g).to(DEV)
+    nv_t = None if nvalid is None else torch.tensor([max(1, int(M * nvalid))], dtype=torch.int32, device=DEV)
+    nv = None if nv_t is None else int(nv_t)
+    req = F_hl.BnTiles(nv_t)
+    if K2:
+        a2 = (3.0 + torch.randn(M, K2, generator=g)).to(DEV)              # a mean far from zero: cancellation in E[x^2] - mean^2
+        w2 = (torch.randn(Nn, K2, generator=g) / K2 ** 0.5).to(DEV)
+        y = F_hl.dense2(a1, w1, a2, w2, bias, bn=req)
+        y_plain = F_hl.dense2(a1, w1, a2, w2, bias)
+    else:
+        y = F_hl.dense(a1, w1, bias, bn=req)
+        y_plain = F_hl.dense(a1, w1, bias)
+    assert torch.equal(y, y_plain)                                        # the statistics do not change the output
+    assert req.part is not None and req.matches(y, nv_t)
+    mean, var = _merge_tiles(req.part, M, Nn, nv)
+    yd = y[:nv].double().cpu() if nv is not None else y.double().cpu()
+    close(mean.float(), yd.mean(0).float(), rtol=1e-5, atol=1e-6)
+    close(var.float(), yd.var(0, unbiased=False).float(), rtol=1e-5, atol=1e-7)
+    # accumulate launch: statistics of the FINAL values
+    req2 = F_hl.BnTiles(nv_t)
+    y2 = y.clone()
+    F_hl.dense(a1, w1, None, out=y2, accumulate=True, bn=req2)
+    mean2, var2 = _merge_tiles(req2.part, M, Nn, nv)
+    y2d = y2[:nv].double().cpu() if nv is not None else y2.double().cpu()
+    close(mean2.float(), y2d.mean(0).float(), rtol=1e-5, atol=1e-6)
+    close(var2.float(), y2d.var(0, unbiased=False).float(), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("M,Nn,K", [(24001, 64, 64), (3000, 256, 128), (77000, 128, 64), (50, 64, 64)])
+@pytest.mark.parametrize("nvalid", [None, 0.8])
+def test_bn_from_epilogue_tiles_equals_bn_with_own_statistics(M, Nn, K, nvalid):
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, K, generator=g).to(DEV).requires_grad_(True)
+    w = (torch.randn(Nn, K, generator=g) / K ** 0.5).to(DEV).requires_grad_(True)
+    b = torch.randn(Nn, generator=g).to(DEV).requires_grad_(True)
+    gamma = torch.rand(Nn, generator=g).add(0.5).to(DEV).requires_grad_(True)
+    beta = torch.randn(Nn, generator=g).to(DEV).requires_grad_(True)
+    nv_t = None if nvalid is None else torch.tensor([int(M * nvalid)], dtype=torch.int32, device=DEV)
+    dy = torch.randn(M, Nn, generator=g).to(DEV)
+    res = []
+    for use_tiles in (True, False):
+        rm, rv = torch.zeros(Nn, device=DEV), torch.ones(Nn, device=DEV)
+        cnt = torch.zeros((), dtype=torch.int64, device=DEV)
+        with F_hl.bn_stats_from_epilogue(nv_t, enabled=use_tiles) as req:
+            h = F_hl.linear(x, w, b)
+        assert (req is not None and req.part is not None) == use_tiles
+        y, stats = F_hl.bn_act_train(h, gamma, beta, 1e-5, 0.0, nv_t, rm, rv, 0.1, cnt, None, req)
+        grads = torch.autograd.grad(y, (x, w, b, gamma, beta), dy)
+        res.append((y, stats, rm, rv, *grads))
+        assert int(cnt) == 1
+    for a, c in zip(*res):
+        close(a, c, rtol=1e-5, atol=1e-6)
+
+
+def test_training_step_with_and_without_epilogue_statistics(monkeypatch):
+    """Whole model, forward + backward: the epilogue statistics change nothing beyond fp32 rounding."""
+    from hlhgat_b200.lib import Hodge_ST_Model as M
+    from hlhgat_b200.workloads import WORKLOADS
+    from hlhgat_b200.training import Capacity, pad_levels, StaticBatch
+    wl = WORKLOADS["zinc"]
+    raw = wl.make(64, 0)
+    caps = [Capacity.covering([raw[l]]) for l in range(wl.levels)]
+    host = pad_levels(raw, caps, deg_eps=wl.deg_eps)
+    out = []
+    for flag in (True, False):
+        monkeypatch.setattr(F_hl, "_BN_EPILOGUE", flag)
+        torch.manual_seed(0)
+        model = getattr(M, wl.model)(**wl.ctor).to(DEV).train()
+        batch = StaticBatch(host, torch.device(DEV))
+        H.simplex.clear_caches()
+        loss = wl.loss(model, batch)
+        loss.backward()
+        out.append((loss.detach(), [p.grad.clone() for p in model.parameters()]))
+    close(out[0][0], out[1][0], rtol=1e-5)
+    for ga, gb in zip(out[0][1], out[1][1]):
+        close(ga, gb, rtol=2e-4, atol=1e-5 * float(gb.abs().max()) + 1e-7)
