@@ -155,43 +155,67 @@ __global__ void bn_stats_final_kernel(const double* __restrict__ partial, int nb
   }
 }
 
-// Statistics from the per-32-row-block (mean | M2) pairs the producing GEMM's epilogue wrote (hl_gemm2_bn_tf32x3): Chan's
-// parallel-variance merge in fp64.  Thread (ks, cl) merges the blocks ks, ks + 32, ... of column c0 + cl in ascending order,
-// then the 32 partial results are merged in ascending ks: a fixed order, reproducible.
-__global__ void bn_stats_final_tiles_kernel(const float* __restrict__ part, int32_t nrows_cap, const int32_t* __restrict__ nvalid,
-                                            int32_t width, float* __restrict__ stats, float* __restrict__ running_mean,
-                                            float* __restrict__ running_var, float momentum,
-                                            long long* __restrict__ batches_tracked) {
-  if (batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *batches_tracked += 1;
-  __shared__ double sh[3][32][kBnFinalCols];
-  const int32_t nrows = nvalid ? min(__ldg(nvalid), nrows_cap) : nrows_cap;
-  const int nblk = (nrows_cap + 31) / 32;
-  const int cl = threadIdx.x & (kBnFinalCols - 1), ks = threadIdx.x / kBnFinalCols;
-  const int c = blockIdx.x * kBnFinalCols + cl;
-  double n = 0.0, mean = 0.0, m2 = 0.0;
-  if (c < width)
-    for (int k = ks; k < nblk; k += 32) {
-      const int cnt = max(0, min(32, nrows - k * 32));
-      if (cnt == 0) break;                                            // blocks are ordered by row: nothing valid beyond
-      const double nb = (double)cnt, mb = (double)part[((int64_t)k * 2 + 0) * width + c], qb = (double)part[((int64_t)k * 2 + 1) * width + c];
-      const double tot = n + nb, delta = mb - mean;
-      mean += delta * nb / tot;
-      m2 += qb + delta * delta * n * nb / tot;
-      n = tot;
-    }
-  sh[0][ks][cl] = n; sh[1][ks][cl] = mean; sh[2][ks][cl] = m2;
+// Statistics from the per-32-row-block (mean | M2) pairs the producing GEMM's epilogue wrote (hl_gemm2_bn_tf32x3), merged
+// in fp64 in two passes of independent loads (no serial Chan chain: a 50,000-row activation has 1,563 blocks):
+//   mean = sum_b n_b mean_b / n,      M2 = sum_b (M2_b + n_b (mean_b - mean)^2)
+// 1024 threads = 4 columns x 256 block slices; slice sums are combined in a fixed order (shuffle over the 8 slices of a
+// warp, then the 32 warps serially): reproducible.
+constexpr int kBnTileCols = 4, kBnTileSlices = 256, kBnTileHold = 8;
+__device__ __forceinline__ double bn_tiles_reduce(double v, double (*sh)[kBnTileCols], int cl) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  __syncthreads();                                        // the previous use of sh is over
+  if ((threadIdx.x & 31) < kBnTileCols) sh[threadIdx.x >> 5][cl] = v;
   __syncthreads();
-  if (ks != 0 || c >= width) return;
-  n = 0.0; mean = 0.0; m2 = 0.0;
-  for (int j = 0; j < 32; ++j) {
-    const double nb = sh[0][j][cl];
-    if (nb == 0.0) continue;
-    const double tot = n + nb, delta = sh[1][j][cl] - mean;
-    mean += delta * nb / tot;
-    m2 += sh[2][j][cl] + delta * delta * n * nb / tot;
-    n = tot;
+  double t = 0.0;
+#pragma unroll 8
+  for (int w = 0; w < kBnTileSlices / 8; ++w) t += sh[w][cl];
+  return t;
+}
+
+__global__ void __launch_bounds__(kBnTileCols* kBnTileSlices)
+bn_stats_final_tiles_kernel(const float* __restrict__ part, int32_t nrows_cap, const int32_t* __restrict__ nvalid,
+                            int32_t width, float* __restrict__ stats, float* __restrict__ running_mean,
+                            float* __restrict__ running_var, float momentum, long long* __restrict__ batches_tracked) {
+  if (batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *batches_tracked += 1;
+  __shared__ double sh[kBnTileSlices / 8][kBnTileCols];
+  // every load of the launch is issued up front (the row count and up to kBnTileHold (mean, M2) pairs per thread: enough
+  // for 65,536 rows); blocks past *nvalid hold zeros and get weight 0, so the loads do not wait for the row count
+  const int nblk = (nrows_cap + 31) / 32;
+  const int cl = threadIdx.x & (kBnTileCols - 1), ks = threadIdx.x / kBnTileCols;
+  const int c = min(blockIdx.x * kBnTileCols + cl, width - 1);       // overhanging columns: duplicate work, no store
+  const bool store = blockIdx.x * kBnTileCols + cl < width && ks == 0;
+  const float* p = part + c;
+  float mk[kBnTileHold], qk[kBnTileHold];
+#pragma unroll
+  for (int u = 0; u < kBnTileHold; ++u) {
+    const int k = ks + u * kBnTileSlices;
+    mk[u] = k < nblk ? __ldg(p + (int64_t)k * 2 * width) : 0.f;
+    qk[u] = k < nblk ? __ldg(p + ((int64_t)k * 2 + 1) * width) : 0.f;
   }
-  if (n > 0.0) {
+  const int32_t nrows = nvalid ? min(__ldg(nvalid), nrows_cap) : nrows_cap;
+  double a = 0.0;
+#pragma unroll
+  for (int u = 0; u < kBnTileHold; ++u)
+    a += (double)max(0, min(32, nrows - (ks + u * kBnTileSlices) * 32)) * (double)mk[u];
+  for (int k = ks + kBnTileHold * kBnTileSlices; k < nblk; k += kBnTileSlices)
+    a += (double)max(0, min(32, nrows - k * 32)) * (double)__ldg(p + (int64_t)k * 2 * width);
+  const double n = (double)nrows;
+  const double mean = nrows > 0 ? bn_tiles_reduce(a, sh, cl) / n : 0.0;
+  double q = 0.0;
+#pragma unroll
+  for (int u = 0; u < kBnTileHold; ++u) {
+    const double d = (double)mk[u] - mean;
+    q += (double)qk[u] + (double)max(0, min(32, nrows - (ks + u * kBnTileSlices) * 32)) * d * d;
+  }
+  for (int k = ks + kBnTileHold * kBnTileSlices; k < nblk; k += kBnTileSlices) {
+    const double d = (double)__ldg(p + (int64_t)k * 2 * width) - mean;
+    q += (double)__ldg(p + ((int64_t)k * 2 + 1) * width) + (double)max(0, min(32, nrows - k * 32)) * d * d;
+  }
+  const double m2 = bn_tiles_reduce(q, sh, cl);
+  if (!store) return;
+  if (nrows > 0) {
     const float fm = (float)mean, var = (float)fmax(m2 / n, 0.0);
     stats[c] = fm;
     stats[width + c] = var;
@@ -456,7 +480,7 @@ extern "C" int hl_bn_act_fwd_tiles(const float* x, int64_t ld_x, int32_t nrows, 
   using namespace hl;
   if (nrows < 1 || width < 1 || !x || !y || !stats || !bn_part) return HL_ERR_INVALID;
   cudaStream_t st = as_stream(stream);
-  bn_stats_final_tiles_kernel<<<(width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st>>>(
+  bn_stats_final_tiles_kernel<<<(width + kBnTileCols - 1) / kBnTileCols, kBnTileCols * kBnTileSlices, 0, st>>>(
       bn_part, nrows, nvalid, width, stats, running_mean, running_mean ? running_var : nullptr, momentum,
       reinterpret_cast<long long*>(num_batches_tracked));
   HL_LAUNCH_CHECK("bn_stats_final_tiles_kernel");

@@ -419,6 +419,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // (thread = row) -> a padded per-warp staging tile in shared memory (the ring is idle by now) -> global memory with
     // 8 lanes per row, so a warp instruction moves four complete 128-byte row segments (full sectors) instead of 32
     // half-filled ones; in accumulate mode the old values are fetched the same way and BEFORE the tcgen05.ld wait.
+    int bn_rows = P.M;                                                // BatchNorm statistics: rows they cover (load in flight under the wait)
+    if (MODE == 0 && P.bn_part && P.bn_nvalid) bn_rows = min(__ldg(P.bn_nvalid), P.M);
     gm_mbar_wait(acc_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float* Cbase = P.C + (MODE == 1 ? (int64_t)blockIdx.z * P.split_stride : 0);
@@ -478,8 +480,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           fin[it] = v;
         }
         if (MODE == 0 && P.bn_part && m0 + quad * 32 < P.M) {             // (warp-uniform) blocks past the last row do not exist
-          const int nvr = P.bn_nvalid ? min(__ldg(P.bn_nvalid), P.M) : P.M;
-          gm_bn_block_stats(fin, m0 + quad * 32, sub_row, nvr, P.bn_part, (int64_t)(m0 / 32 + quad), P.N, col, col_ok);
+          gm_bn_block_stats(fin, m0 + quad * 32, sub_row, bn_rows, P.bn_part, (int64_t)(m0 / 32 + quad), P.N, col, col_ok);
         }
         __syncwarp();                                                 // the staging tile is reused by the next chunk
         continue;
@@ -651,6 +652,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
     float* stage_tile = staging + (size_t)(warp - 6) * 32 * kPsPitch;
     const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
     const bool vec_ok = (P.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
+    const int bn_rows = (P.bn_part && P.bn_nvalid) ? min(__ldg(P.bn_nvalid), P.M) : P.M;   // rows the BatchNorm statistics cover
     int it = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
@@ -706,8 +708,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
             fin[i8] = v;
           }
           if (P.bn_part && m0 + quad * 32 < P.M) {
-            const int nvr = P.bn_nvalid ? min(__ldg(P.bn_nvalid), P.M) : P.M;
-            gm_bn_block_stats(fin, m0 + quad * 32, sub_row, nvr, P.bn_part, (int64_t)(m0 / 32 + quad), P.N, col, col_ok);
+            gm_bn_block_stats(fin, m0 + quad * 32, sub_row, bn_rows, P.bn_part, (int64_t)(m0 / 32 + quad), P.N, col, col_ok);
           }
           __syncwarp();
           continue;

@@ -573,8 +573,11 @@ def test_bn_from_epilogue_tiles_equals_bn_with_own_statistics(M, Nn, K, nvalid):
         grads = torch.autograd.grad(y, (x, w, b, gamma, beta), dy)
         res.append((y, stats, rm, rv, *grads))
         assert int(cnt) == 1
-    for a, c in zip(*res):
-        close(a, c, rtol=1e-5, atol=1e-6)
+    for i, (a, c) in enumerate(zip(*res)):                                # statistics differ in the last fp32 bit at most
+        if i == 6:            # d(bias of the Linear): analytically zero behind a BatchNorm, both are cancellation noise
+            assert float(a.abs().max()) < 1e-6 * M + 1e-5 and float(c.abs().max()) < 1e-6 * M + 1e-5
+            continue
+        close(a, c, rtol=1e-5, atol=1e-6 * max(1.0, float(c.detach().abs().max())))
 
 
 def test_training_step_with_and_without_epilogue_statistics(monkeypatch):
