@@ -59,6 +59,21 @@ __device__ __forceinline__ void gm_tma_load_2d(void* dst, const CUtensorMap* map
       "l"(map), "r"(gm_smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// shared memory tile (written through the generic proxy, fenced) -> global memory through the tensor map; `add`: the tile
+// is ADDED to what global memory holds (a reduction performed by the memory system: the SM never reads the old values)
+__device__ __forceinline__ void gm_tma_store_2d(const void* src, const CUtensorMap* map, int c0, int c1, bool add) {
+  if (add)
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                 "r"(gm_smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(gm_smem_u32(src)),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void gm_tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void gm_tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void gm_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -173,6 +188,7 @@ struct GemmParams {
   int32_t x_tiles_each;         // wgrad with TWO X operands (map_bhi, map_blo): column tiles per operand (0 = one operand)
   float* bn_part;               // forward: per 32-row block BatchNorm statistics of the output [ceil(M/32)][2][N] (mean | M2), or NULL
   const int32_t* bn_nvalid;     // device row count the statistics cover (rows beyond are padding), or NULL = M
+  int32_t tma_c;                // persistent kernel: the output has a tensor map (map_c): 32 x 32 chunks leave through TMA
 };
 
 // MODE 0: C = A[M,K] B[N,K]^T, both K-major, B pre-split (map_b = hi, map_b2 = lo).
@@ -518,23 +534,32 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 // warps drain accumulator b (TMEM -> registers -> padded staging tile -> full 128-byte row segments) while the MMA warp
 // already fills accumulator 1 - b with the next tile.
 //   warp 0      TMA producer          warp 1      tcgen05.mma issue (one lane)
-//   warps 2-5   A converters          warps 6-9   epilogue
+//   warps 2-5   A converters          warps 6-13  epilogue (two per TMEM lane quadrant, alternate 32-column chunks)
+//
+// Epilogue of a 32 x 32 chunk: TMEM -> registers (thread = row) -> (+ bias) -> a 4 KB staging tile in the 128-byte
+// swizzle -> ONE TMA store of the tile (cp.async.bulk.tensor, clipped at the matrix edge by the tensor map); in
+// accumulate mode a TMA reduce-add, so the old values are never read by the SM.  (The register epilogue that came
+// before it -- read the tile back 8 lanes per row, fetch the old values, add, store -- kept 16 KB of loads in flight per
+// SM and reached 45 % of the HBM floor on the output-bound shapes [229944, 128] x [128, 416..672] of the TSP step,
+// tools/dense_shapes_probe.py.)  The register path remains for launches that want the BatchNorm statistics of the final
+// values, for the chunk that straddles the end of a column tile, and for outputs a tensor map cannot describe.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kPsThreads = 320;
-constexpr int kPsPitch = 36;                                  // floats per staged epilogue row (144 B: conflict-free float4)
+constexpr int kPsEpiWarps = 8;
+constexpr int kPsThreads = 64 + kGmConvThreads + 32 * kPsEpiWarps;
+constexpr int kPsStageFloats = 32 * 32;                       // one staged chunk: 32 rows x 128 B, 128-byte swizzle
 
 __global__ void __launch_bounds__(kPsThreads, 1)
 gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                               const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_a2,
-                              const GemmParams P) {
+                              const __grid_constant__ CUtensorMap map_c, const GemmParams P) {
   extern __shared__ __align__(1024) unsigned char gm_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bn = P.bn, stages = P.stages;
   const uint32_t a_bytes = kGmBM * kGmBK * 4, b_bytes = (uint32_t)bn * kGmBK * 4;
   const uint32_t stage_bytes = a_bytes + 2 * b_bytes;
   unsigned char* base = gm_smem;
-  float* staging = reinterpret_cast<float*>(base + (size_t)stages * stage_bytes);          // [4 warps][32 rows][kPsPitch]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(staging) + 4 * 32 * kPsPitch * 4);
+  float* staging = reinterpret_cast<float*>(base + (size_t)stages * stage_bytes);          // [8 warps][32 rows][32], 1 KB aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(staging) + kPsEpiWarps * kPsStageFloats * 4);
   uint64_t* full_bar = bars;                 // [stages]  TMA bytes landed
   uint64_t* conv_bar = bars + stages;        // [stages]  A split written to tensor memory
   uint64_t* empty_bar = bars + 2 * stages;   // [stages]  MMAs of the stage retired
@@ -551,7 +576,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
     }
     for (int b = 0; b < 2; ++b) {
       gm_mbar_init(&acc_full[b], 1);
-      gm_mbar_init(&acc_empty[b], 4);                               // one arrival per epilogue warp
+      gm_mbar_init(&acc_empty[b], kPsEpiWarps);                     // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -649,17 +674,21 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
   } else {
     // ------------------------------------ epilogue ------------------------------------
     const int quad = warp & 3;                                       // TMEM lane quadrant this warp may read
-    float* stage_tile = staging + (size_t)(warp - 6) * 32 * kPsPitch;
+    const int half = (warp - 6) >> 2;                                // the two warps of a quadrant take alternate chunks
+    float* stage_tile = staging + (size_t)(warp - 6) * kPsStageFloats;
+    unsigned char* stage_row = reinterpret_cast<unsigned char*>(stage_tile) + lane * 128;   // thread = row of the chunk
     const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
     const bool vec_ok = (P.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
+    const bool bias_vec = P.bias && (reinterpret_cast<uintptr_t>(P.bias) & 15) == 0;
     const int bn_rows = (P.bn_part && P.bn_nvalid) ? min(__ldg(P.bn_nvalid), P.M) : P.M;   // rows the BatchNorm statistics cover
+    bool tma_pending = false;                                        // a TMA store may still be reading the staging tile
     int it = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
       const int m0 = (tile / P.tiles_n) * kGmBM, n0 = (tile % P.tiles_n) * bn;
       gm_mbar_wait(&acc_full[b], (uint32_t)((it >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int c = 0; c < bn; c += 32) {
+      for (int c = 32 * half; c < bn; c += 64) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * P.acc_stride + c);
         asm volatile(
@@ -673,6 +702,34 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
             : "r"(taddr)
             : "memory");
         if (vec_ok) {
+          // whole chunk inside this column tile (or the tile is the last one: the tensor map clips at column N)
+          const bool by_tma = P.tma_c && !P.bn_part && (c + 32 <= bn || n0 + bn >= P.N);
+          if (tma_pending) {                                          // the previous store has read the staging tile
+            if (lane == 0) gm_tma_store_wait_read();
+            __syncwarp();
+            tma_pending = false;
+          }
+          if (by_tma) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                     __uint_as_float(r[4 * j + 3]));
+              const int col = n0 + c + 4 * j;
+              if (P.bias && col + 3 < P.N) {                          // the same address in every lane: one broadcast load
+                const float4 bv = bias_vec ? __ldg(reinterpret_cast<const float4*>(P.bias + col))
+                                           : make_float4(__ldg(P.bias + col), __ldg(P.bias + col + 1), __ldg(P.bias + col + 2),
+                                                         __ldg(P.bias + col + 3));
+                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+              }
+              *reinterpret_cast<float4*>(stage_row + ((j ^ (lane & 7)) << 4)) = v;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA engine
+            __syncwarp();
+            if (lane == 0 && m0 + quad * 32 < P.M && n0 + c < P.N) gm_tma_store_2d(stage_tile, &map_c, n0 + c, m0 + quad * 32, P.accumulate != 0);
+            tma_pending = true;
+            continue;
+          }
           const int col = n0 + c + sub_col;
           const bool col_ok = col + 3 < P.N && c + sub_col < bn;
           float4 old[8];
@@ -686,22 +743,22 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
           }
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
           if (P.bias && col_ok) {
-            if ((reinterpret_cast<uintptr_t>(P.bias) & 15) == 0) bv = __ldg(reinterpret_cast<const float4*>(P.bias + col));
+            if (bias_vec) bv = __ldg(reinterpret_cast<const float4*>(P.bias + col));
             else bv = make_float4(__ldg(P.bias + col), __ldg(P.bias + col + 1), __ldg(P.bias + col + 2), __ldg(P.bias + col + 3));
           }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          float* mine = stage_tile + lane * kPsPitch;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(mine + j) =
-                make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stage_row + ((j ^ (lane & 7)) << 4)) =
+                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
           __syncwarp();
           float4 fin[8];
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8) {
             const int lr = i8 * 4 + sub_row;
             const int rr = m0 + quad * 32 + lr;
-            float4 v = *reinterpret_cast<const float4*>(stage_tile + lr * kPsPitch + sub_col);
+            float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(stage_tile) + lr * 128 +
+                                                        (((lane & 7) ^ (lr & 7)) << 4));
             v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
             if (P.accumulate) { v.x += old[i8].x; v.y += old[i8].y; v.z += old[i8].z; v.w += old[i8].w; }
             if (col_ok && rr < P.M) *reinterpret_cast<float4*>(P.C + (int64_t)rr * P.ldc + col) = v;
@@ -728,8 +785,9 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) gm_mbar_arrive(&acc_empty[b]);                  // this warp's quadrant of accumulator b is free again
+      if (lane == 0) gm_mbar_arrive(&acc_empty[b]);                  // this warp's chunks of accumulator b are free again
     }
+    if (tma_pending && lane == 0) gm_tma_store_wait_all();           // the staging tile must outlive the last store
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -928,15 +986,19 @@ extern "C" int hl_gemm2_bn_tf32x3(const float* A, int64_t lda, int32_t K, const 
   // (measured: [24144,64] x [64,64] 5.6 vs 6.4 us, [24144,256] x [256,256] 25.2 vs 18.4 us)
   if (persistent && use_ts && bn <= 128 && (persistent == 2 || ctas > 2 * 148)) {
     const int acc_stride = (bn + 31) / 32 * 32;
-    int ps = (int)((227 * 1024 - 1024 - 4 * 32 * kPsPitch * 4 - 256) / stage_bytes);
+    int ps = (int)((227 * 1024 - 1024 - kPsEpiWarps * kPsStageFloats * 4 - 256) / stage_bytes);
     if (ps > 6) ps = 6;
     while (ps > 2 && 2 * acc_stride + 64 * ps > 512) --ps;
     if (ps > num_kb && num_kb >= 2) ps = num_kb;
     if (ps >= 2 && 2 * acc_stride + 64 * ps <= 512) {
       int cols = 32;
       while (cols < 2 * acc_stride + 64 * ps) cols <<= 1;
-      const size_t smem_ps = (size_t)ps * stage_bytes + 4 * 32 * kPsPitch * 4 + (3 * ps + 5) * sizeof(uint64_t) + 1024;
-      CUtensorMap pa, pbh, pbl, pa2;
+      const size_t smem_ps = (size_t)ps * stage_bytes + kPsEpiWarps * kPsStageFloats * 4 + (3 * ps + 5) * sizeof(uint64_t) + 1024;
+      CUtensorMap pa, pbh, pbl, pa2, pc;
+      // the output through a tensor map of 32 x 32 boxes (HL_GEMM_TMA_STORE=0: the register epilogue for every chunk)
+      static int tma_store = -1;
+      if (tma_store < 0) { const char* e = getenv("HL_GEMM_TMA_STORE"); tma_store = e ? atoi(e) : 1; }
+      const bool c_map = tma_store && ldc % 4 == 0 && aligned_to(C, 16) && make_map(&pc, C, M, N, ldc, 32, 32);
       if (!make_map(&pa, A, M, K, lda, kGmBM) || !make_map(&pbh, Bhi, N, Ktot, ldb, bn) || !make_map(&pbl, Blo, N, Ktot, ldb, bn))
         return 1;
       if (K2 > 0) { if (!make_map(&pa2, A2, M, K2, lda2, kGmBM)) return 1; }
@@ -949,18 +1011,19 @@ extern "C" int hl_gemm2_bn_tf32x3(const float* A, int64_t lda, int32_t K, const 
       Q.bias = bias; Q.C = C; Q.ldc = ldc; Q.accumulate = accumulate; Q.k_per_split = 0; Q.split_stride = 0;
       Q.tmem_a_col = 2 * acc_stride; Q.colsum_ws = nullptr; Q.conv_groups = 1;
       Q.kb_first = K2 > 0 ? kb_first : 0x7fffffff;
-      Q.x_tiles_each = 0; Q.bn_part = bn_part; Q.bn_nvalid = bn_nvalid;
+      Q.x_tiles_each = 0; Q.bn_part = bn_part; Q.bn_nvalid = bn_nvalid; Q.tma_c = c_map ? 1 : 0;
       Q.tiles_n = ntiles; Q.num_tiles = ((M + kGmBM - 1) / kGmBM) * ntiles; Q.acc_stride = acc_stride;
       const int sms = device_sm_count();
       const int grid_ps = Q.num_tiles < sms ? Q.num_tiles : sms;
-      gemm_tf32x3_persistent_kernel<<<grid_ps, kPsThreads, smem_ps, as_stream(stream)>>>(pa, pbh, pbl, pa2, Q);
+      if (!c_map) pc = pa;
+      gemm_tf32x3_persistent_kernel<<<grid_ps, kPsThreads, smem_ps, as_stream(stream)>>>(pa, pbh, pbl, pa2, pc, Q);
       HL_LAUNCH_CHECK("gemm_tf32x3_persistent_kernel");
       return HL_OK;
     }
   }
   GemmParams P;
   P.M = M; P.N = N; P.K = Ktot; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
-  P.num_tiles = 0; P.tiles_n = 1; P.acc_stride = 0; P.x_tiles_each = 0; P.bn_part = bn_part; P.bn_nvalid = bn_nvalid;
+  P.num_tiles = 0; P.tiles_n = 1; P.acc_stride = 0; P.x_tiles_each = 0; P.bn_part = bn_part; P.bn_nvalid = bn_nvalid; P.tma_c = 0;
   P.bias = bias; P.C = C; P.ldc = ldc; P.accumulate = accumulate; P.k_per_split = 0; P.split_stride = 0;
   P.tmem_a_col = tmem_a_col; P.colsum_ws = nullptr; P.conv_groups = 1;
   P.kb_first = K2 > 0 ? kb_first : 0x7fffffff;
@@ -1149,7 +1212,7 @@ static int wgrad_launch(const float* g, int64_t ld_g, const float* x, int64_t ld
     HL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   GemmParams P;
-  P.num_tiles = 0; P.tiles_n = 1; P.acc_stride = 0; P.x_tiles_each = x2 ? ntiles : 0; P.bn_part = nullptr; P.bn_nvalid = nullptr;
+  P.num_tiles = 0; P.tiles_n = 1; P.acc_stride = 0; P.x_tiles_each = x2 ? ntiles : 0; P.bn_part = nullptr; P.bn_nvalid = nullptr; P.tma_c = 0;
   P.M = fo; P.N = fi; P.K = nrows; P.bn = bn; P.stages = stages; P.tmem_cols = tmem_cols;
   P.bias = nullptr; P.C = reinterpret_cast<float*>(workspace); P.ldc = fi_tot; P.accumulate = 0;
   P.k_per_split = k_per_split; P.split_stride = (int64_t)fo * fi_tot; P.tmem_a_col = tmem_a_col;

@@ -584,11 +584,10 @@ def test_training_step_with_and_without_epilogue_statistics(monkeypatch):
     """Whole model, forward + backward: the epilogue statistics change nothing beyond fp32 rounding."""
     from hlhgat_b200.lib import Hodge_ST_Model as M
     from hlhgat_b200.workloads import WORKLOADS
-    from hlhgat_b200.training import Capacity, pad_levels, StaticBatch
+    from hlhgat_b200.training import Capacity, pad_batch, StaticBatch
     wl = WORKLOADS["zinc"]
     raw = wl.make(64, 0)
-    caps = [Capacity.covering([raw[l]]) for l in range(wl.levels)]
-    host = pad_levels(raw, caps, deg_eps=wl.deg_eps)
+    host = pad_batch(raw, Capacity.covering([raw]), deg_eps=wl.deg_eps)
     out = []
     for flag in (True, False):
         monkeypatch.setattr(F_hl, "_BN_EPILOGUE", flag)
