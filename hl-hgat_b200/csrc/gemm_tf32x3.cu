@@ -710,17 +710,19 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
             tma_pending = false;
           }
           if (by_tma) {
+            // bias of column n0 + c + lane, fetched under the TMEM read and handed round by shuffles (thread = row needs all 32)
+            float bias_l = 0.f;
+            if (P.bias && n0 + c + lane < P.N) bias_l = __ldg(P.bias + n0 + c + lane);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                                      __uint_as_float(r[4 * j + 3]));
-              const int col = n0 + c + 4 * j;
-              if (P.bias && col + 3 < P.N) {                          // the same address in every lane: one broadcast load
-                const float4 bv = bias_vec ? __ldg(reinterpret_cast<const float4*>(P.bias + col))
-                                           : make_float4(__ldg(P.bias + col), __ldg(P.bias + col + 1), __ldg(P.bias + col + 2),
-                                                         __ldg(P.bias + col + 3));
-                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+              if (P.bias) {
+                v.x += __shfl_sync(0xffffffffu, bias_l, 4 * j);
+                v.y += __shfl_sync(0xffffffffu, bias_l, 4 * j + 1);
+                v.z += __shfl_sync(0xffffffffu, bias_l, 4 * j + 2);
+                v.w += __shfl_sync(0xffffffffu, bias_l, 4 * j + 3);
               }
               *reinterpret_cast<float4*>(stage_row + ((j ^ (lane & 7)) << 4)) = v;
             }
