@@ -38,6 +38,13 @@ class SplitDesc(C.Structure):
                 ("rows", _i32), ("cols", _i32), ("transpose", _i32), ("reserved", _i32)]
 
 
+class WgradReduceDesc(C.Structure):
+    _fields_ = [("partial", _vp), ("cs_partial", _vp), ("dw", _vp), ("dw2", _vp), ("dbias", _vp),
+                ("split_stride", _i64), ("ld_dw", _i64), ("ld_dw2", _i64),
+                ("splits", _i32), ("fo", _i32), ("fi", _i32), ("fi_first", _i32), ("accumulate", _i32),
+                ("accumulate_bias", _i32), ("block_start", _i32), ("reserved", _i32)]
+
+
 class Hodge1Operator(C.Structure):
     _fields_ = [("inc_rowptr", _vp), ("inc_edge", _vp), ("tail", _vp), ("head", _vp), ("edge_scale", _vp),
                 ("n_nodes", _i32), ("n_edges", _i32)]
@@ -81,6 +88,9 @@ _SIGNATURES = {
     "hl_wgrad2_tf32x3_workspace": (_sz, [_i32, _i32, _i32]),
     "hl_wgrad2_bias_tf32x3": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _i64, C.c_int, _vp, C.c_int,
                                         _vp, _sz, _vp]),
+    "hl_wgrad_deferred_tf32x3": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _i64, C.c_int, _vp, C.c_int,
+                                           _vp, _sz, C.POINTER(WgradReduceDesc), _vp]),
+    "hl_wgrad_reduce_batch": (C.c_int, [C.POINTER(WgradReduceDesc), _i32, _vp]),
     "hl_wgrad_workspace": (_sz, [_i32, _i32, _i32]),
     "hl_wgrad": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, C.c_int, _vp, _sz, _vp]),
     "hl_colsum_workspace": (_sz, [_i32, _i32]),

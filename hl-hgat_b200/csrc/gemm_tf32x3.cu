@@ -1037,12 +1037,13 @@ extern "C" int hl_gemm2_bn_tf32x3(const float* A, int64_t lda, int32_t K, const 
 }
 
 // dw (=|+=) sum over the row splits: 8 lanes per group of 4 consecutive output elements (one float4 per split
-// plane and lane: k = lane, lane + 8, ...; whole 32-byte sectors of every plane), fixed shuffle tree -> deterministic
-__global__ void __launch_bounds__(256)
-gm_split_reduce_kernel(const float* __restrict__ partial, int32_t splits, int64_t split_stride, int32_t fo,
-                       int32_t fi, float* __restrict__ dw, int64_t ld_dw, int accumulate,
-                       const float* __restrict__ cs_partial, float* __restrict__ dbias, int accumulate_bias,
-                       float* __restrict__ dw2, int64_t ld_dw2, int32_t fi_first) {
+// plane and lane: k = lane, lane + 8, ...; whole 32-byte sectors of every plane), fixed shuffle tree -> deterministic.
+// One call handles output group i (all 8 lanes of the group call it together).
+__device__ __forceinline__ void gm_split_reduce_group(const float* __restrict__ partial, int32_t splits, int64_t split_stride,
+                                                      int32_t fo, int32_t fi, float* __restrict__ dw, int64_t ld_dw, int accumulate,
+                                                      const float* __restrict__ cs_partial, float* __restrict__ dbias,
+                                                      int accumulate_bias, float* __restrict__ dw2, int64_t ld_dw2,
+                                                      int32_t fi_first, int64_t i) {
   // fi: columns of a partial plane; with dw2 the plane is [dW1 (fi_first columns) | dW2] and goes to two destinations
   const int64_t n4 = ((int64_t)fo * fi) >> 2;                      // fi % 32 == 0: rows never straddle a float4
   const int64_t c4 = dbias ? (fo >> 2) : 0;                         // + the [splits][fo] column sums of G (bias gradient)
@@ -1050,52 +1051,88 @@ gm_split_reduce_kernel(const float* __restrict__ partial, int32_t splits, int64_
   const int sub = threadIdx.x & 7;
   const bool vec_out = (ld_dw % 4 == 0) && ((reinterpret_cast<uintptr_t>(dw) & 15) == 0) &&
                        (!dw2 || ((ld_dw2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(dw2) & 15) == 0)));
-  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < ((tot4 + 3) & ~(int64_t)3);
-       i += ((int64_t)gridDim.x * blockDim.x) >> 3) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < tot4) {
-      const bool is_cs = i >= n4;
-      const float4* p = is_cs ? reinterpret_cast<const float4*>(cs_partial) + (i - n4) : reinterpret_cast<const float4*>(partial) + i;
-      const int64_t stride4 = is_cs ? (int64_t)(fo >> 2) : (split_stride >> 2);
-      int k = sub;
-      const int planes = is_cs ? 2 * splits : splits;               // column sums: one plane per split and converter group
-      for (; k + 24 < planes; k += 32) {
-        float4 v[4];
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < tot4) {
+    const bool is_cs = i >= n4;
+    const float4* p = is_cs ? reinterpret_cast<const float4*>(cs_partial) + (i - n4) : reinterpret_cast<const float4*>(partial) + i;
+    const int64_t stride4 = is_cs ? (int64_t)(fo >> 2) : (split_stride >> 2);
+    int k = sub;
+    const int planes = is_cs ? 2 * splits : splits;               // column sums: one plane per split and converter group
+    for (; k + 24 < planes; k += 32) {
+      float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __ldg(p + (int64_t)(k + 8 * u) * stride4);
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(p + (int64_t)(k + 8 * u) * stride4);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
-      }
-      for (; k < planes; k += 8) {
-        const float4 v = __ldg(p + (int64_t)k * stride4);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      }
+      for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
     }
+    for (; k < planes; k += 8) {
+      const float4 v = __ldg(p + (int64_t)k * stride4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
 #pragma unroll
-    for (int m = 1; m < 8; m <<= 1) {
-      s.x += __shfl_xor_sync(0xffffffffu, s.x, m);
-      s.y += __shfl_xor_sync(0xffffffffu, s.y, m);
-      s.z += __shfl_xor_sync(0xffffffffu, s.z, m);
-      s.w += __shfl_xor_sync(0xffffffffu, s.w, m);
+  for (int m = 1; m < 8; m <<= 1) {
+    s.x += __shfl_xor_sync(0xffffffffu, s.x, m);
+    s.y += __shfl_xor_sync(0xffffffffu, s.y, m);
+    s.z += __shfl_xor_sync(0xffffffffu, s.z, m);
+    s.w += __shfl_xor_sync(0xffffffffu, s.w, m);
+  }
+  if (sub == 0 && i >= n4 && i < tot4) {
+    float* q = dbias + ((i - n4) << 2);
+    q[0] = accumulate_bias ? q[0] + s.x : s.x; q[1] = accumulate_bias ? q[1] + s.y : s.y;
+    q[2] = accumulate_bias ? q[2] + s.z : s.z; q[3] = accumulate_bias ? q[3] + s.w : s.w;
+  }
+  if (sub == 0 && i < n4) {
+    const int64_t e = i << 2;
+    const int64_t o = e / fi, c = e - o * fi;
+    float* q = (dw2 && c >= fi_first) ? dw2 + o * ld_dw2 + (c - fi_first) : dw + o * ld_dw + c;
+    if (vec_out) {
+      float4* q4 = reinterpret_cast<float4*>(q);
+      if (accumulate) { const float4 t = *q4; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+      *q4 = s;
+    } else {
+      q[0] = accumulate ? q[0] + s.x : s.x; q[1] = accumulate ? q[1] + s.y : s.y;
+      q[2] = accumulate ? q[2] + s.z : s.z; q[3] = accumulate ? q[3] + s.w : s.w;
     }
-    if (sub == 0 && i >= n4 && i < tot4) {
-      float* q = dbias + ((i - n4) << 2);
-      q[0] = accumulate_bias ? q[0] + s.x : s.x; q[1] = accumulate_bias ? q[1] + s.y : s.y;
-      q[2] = accumulate_bias ? q[2] + s.z : s.z; q[3] = accumulate_bias ? q[3] + s.w : s.w;
+  }
+}
+
+__device__ __forceinline__ int64_t gm_split_reduce_groups(int32_t fo, int32_t fi, bool with_bias) {
+  const int64_t tot4 = (((int64_t)fo * fi) >> 2) + (with_bias ? (fo >> 2) : 0);
+  return (tot4 + 3) & ~(int64_t)3;                                // whole shuffle groups of a warp
+}
+
+__global__ void __launch_bounds__(256)
+gm_split_reduce_kernel(const float* __restrict__ partial, int32_t splits, int64_t split_stride, int32_t fo,
+                       int32_t fi, float* __restrict__ dw, int64_t ld_dw, int accumulate,
+                       const float* __restrict__ cs_partial, float* __restrict__ dbias, int accumulate_bias,
+                       float* __restrict__ dw2, int64_t ld_dw2, int32_t fi_first) {
+  const int64_t groups = gm_split_reduce_groups(fo, fi, dbias != nullptr);
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < groups; i += ((int64_t)gridDim.x * blockDim.x) >> 3)
+    gm_split_reduce_group(partial, splits, split_stride, fo, fi, dw, ld_dw, accumulate, cs_partial, dbias, accumulate_bias, dw2,
+                          ld_dw2, fi_first, i);
+}
+
+// The reduces of MANY weight gradients in one launch (hl_wgrad_reduce_batch): the descriptors travel as kernel
+// parameters (constant bank, no table upload); work unit = 32 output groups (one 256-thread block pass), the units of
+// descriptor d are [block_start[d], block_start[d + 1]).  Same arithmetic and order as gm_split_reduce_kernel.
+constexpr int kReduceBatchMax = 192;                               // 192 x 96 B + header < the 32 KB parameter limit
+struct ReduceBatch {
+  int32_t n, total_blocks;
+  hl_wgrad_reduce_desc d[kReduceBatchMax];
+};
+__global__ void __launch_bounds__(256) gm_split_reduce_batch_kernel(const __grid_constant__ ReduceBatch B) {
+  for (int blk = blockIdx.x; blk < B.total_blocks; blk += gridDim.x) {
+    int lo = 0, hi = B.n - 1;
+    while (lo < hi) {                                                // last descriptor whose first unit is <= blk
+      const int mid = (lo + hi + 1) >> 1;
+      if (B.d[mid].block_start <= blk) lo = mid; else hi = mid - 1;
     }
-    if (sub == 0 && i < n4) {
-      const int64_t e = i << 2;
-      const int64_t o = e / fi, c = e - o * fi;
-      float* q = (dw2 && c >= fi_first) ? dw2 + o * ld_dw2 + (c - fi_first) : dw + o * ld_dw + c;
-      if (vec_out) {
-        float4* q4 = reinterpret_cast<float4*>(q);
-        if (accumulate) { const float4 t = *q4; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
-        *q4 = s;
-      } else {
-        q[0] = accumulate ? q[0] + s.x : s.x; q[1] = accumulate ? q[1] + s.y : s.y;
-        q[2] = accumulate ? q[2] + s.z : s.z; q[3] = accumulate ? q[3] + s.w : s.w;
-      }
-    }
+    const hl_wgrad_reduce_desc& D = B.d[lo];
+    const int64_t i = ((int64_t)(blk - D.block_start) * 256 + threadIdx.x) >> 3;
+    if (i < gm_split_reduce_groups(D.fo, D.fi, D.dbias != nullptr))   // uniform per group of 8 lanes and per warp of 4 groups
+      gm_split_reduce_group(D.partial, D.splits, D.split_stride, D.fo, D.fi, D.dw, D.ld_dw, D.accumulate, D.cs_partial, D.dbias,
+                            D.accumulate_bias, D.dw2, D.ld_dw2, D.fi_first, i);
   }
 }
 
@@ -1173,7 +1210,7 @@ extern "C" int hl_wgrad_tf32x3(const float* g, int64_t ld_g, const float* x, int
 static int wgrad_launch(const float* g, int64_t ld_g, const float* x, int64_t ld_x, const float* x2, int64_t ld_x2,
                         int32_t nrows, int32_t fo, int32_t fi, float* dw, int64_t ld_dw, float* dw2, int64_t ld_dw2,
                         int accumulate, float* dbias, int accumulate_bias, void* workspace, size_t workspace_bytes,
-                        hl_stream_t stream) {
+                        hl_stream_t stream, hl_wgrad_reduce_desc* defer = nullptr) {
   using namespace hl;
   const int nx = x2 ? 2 : 1;
   if (nrows < 0 || fo < 1 || fi < 1 || !dw || (x2 && !dw2)) return HL_ERR_INVALID;
@@ -1233,6 +1270,13 @@ static int wgrad_launch(const float* g, int64_t ld_g, const float* x, int64_t ld
   else gemm_tf32x3_kernel<1, 0><<<grid, 64 + kGmConvThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
   HL_LAUNCH_CHECK("gemm_tf32x3_kernel<wgrad>");
   const int64_t n = (int64_t)fo * fi_tot;
+  if (defer) {                                                       // the caller sums the splits later (hl_wgrad_reduce_batch)
+    defer->partial = P.C; defer->cs_partial = cs_ws; defer->dw = dw; defer->dw2 = dw2; defer->dbias = fold_bias ? dbias : nullptr;
+    defer->split_stride = P.split_stride; defer->ld_dw = ld_dw; defer->ld_dw2 = ld_dw2;
+    defer->splits = splits; defer->fo = fo; defer->fi = (int32_t)fi_tot; defer->fi_first = fi;
+    defer->accumulate = accumulate; defer->accumulate_bias = accumulate_bias; defer->block_start = 0; defer->reserved = 0;
+    return (dbias && !fold_bias) ? 2 : HL_OK;
+  }
   gm_split_reduce_kernel<<<(int)(((n + (fold_bias ? fo : 0)) * 2 + 255) / 256), 256, 0, as_stream(stream)>>>(
       P.C, splits, P.split_stride, fo, (int32_t)fi_tot, dw, ld_dw, accumulate, cs_ws, fold_bias ? dbias : nullptr, accumulate_bias,
       dw2, ld_dw2, fi);
@@ -1264,4 +1308,42 @@ extern "C" int hl_wgrad2_bias_tf32x3(const float* g, int64_t ld_g, const float* 
   if (!x2 || !dw2) return HL_ERR_INVALID;
   return wgrad_launch(g, ld_g, x1, ld_x1, x2, ld_x2, nrows, fo, fi, dw1, ld_dw1, dw2, ld_dw2, accumulate, dbias, accumulate_bias,
                       workspace, workspace_bytes, stream);
+}
+
+// The weight gradient (one activation: x2 = dw2 = NULL, or two that share g) WITHOUT its split reduce: the partial planes
+// stay in `workspace` (which must live until the reduce has run) and `desc` describes the reduce for
+// hl_wgrad_reduce_batch.  Same return codes as hl_wgrad_bias_tf32x3; on 1 nothing was launched and desc is untouched.
+extern "C" int hl_wgrad_deferred_tf32x3(const float* g, int64_t ld_g, const float* x1, int64_t ld_x1, const float* x2,
+                                        int64_t ld_x2, int32_t nrows, int32_t fo, int32_t fi, float* dw1, int64_t ld_dw1,
+                                        float* dw2, int64_t ld_dw2, int accumulate, float* dbias, int accumulate_bias,
+                                        void* workspace, size_t workspace_bytes, hl_wgrad_reduce_desc* desc, hl_stream_t stream) {
+  if (!desc || (x2 != nullptr) != (dw2 != nullptr)) return HL_ERR_INVALID;
+  return wgrad_launch(g, ld_g, x1, ld_x1, x2, ld_x2, nrows, fo, fi, dw1, ld_dw1, dw2, ld_dw2, accumulate, dbias, accumulate_bias,
+                      workspace, workspace_bytes, stream, desc);
+}
+
+// All deferred reduces in (n / 192 rounded up) launches; `descs` is a HOST array (copied into the kernel parameters).  Two
+// descriptors of one call must not write the same elements (the caller reduces such a pair in separate calls).
+extern "C" int hl_wgrad_reduce_batch(const hl_wgrad_reduce_desc* descs, int32_t n, hl_stream_t stream) {
+  using namespace hl;
+  if (n < 0 || (n > 0 && !descs)) return HL_ERR_INVALID;
+  for (int32_t first = 0; first < n; first += kReduceBatchMax) {
+    ReduceBatch B;
+    B.n = n - first < kReduceBatchMax ? n - first : kReduceBatchMax;
+    int64_t blocks = 0;
+    for (int k = 0; k < B.n; ++k) {
+      B.d[k] = descs[first + k];
+      const int64_t tot4 = (((int64_t)B.d[k].fo * B.d[k].fi) >> 2) + (B.d[k].dbias ? (B.d[k].fo >> 2) : 0);
+      const int64_t groups = (tot4 + 3) & ~(int64_t)3;
+      if (blocks > 0x7fffffff - (groups + 31) / 32) return HL_ERR_INVALID;
+      B.d[k].block_start = (int32_t)blocks;
+      blocks += (groups + 31) / 32;
+    }
+    B.total_blocks = (int32_t)blocks;
+    if (blocks == 0) continue;
+    const int64_t max_grid = (int64_t)device_sm_count() * 8;
+    gm_split_reduce_batch_kernel<<<(int)(blocks < max_grid ? blocks : max_grid), 256, 0, as_stream(stream)>>>(B);
+    HL_LAUNCH_CHECK("gm_split_reduce_batch_kernel");
+  }
+  return HL_OK;
 }

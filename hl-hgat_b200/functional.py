@@ -370,6 +370,106 @@ def dense2(a1, w1, a2, w2, bias=None, out=None, accumulate=False, bn=None):
     return dense(a2, w2, None, out=out, accumulate=True, bn=bn)
 
 
+class WgradReducePlan:
+    """Collects the split reduces of the weight gradients of a training step and runs them in ONE launch.
+
+    A tensor-core weight gradient is two launches: the split-row pass (partial planes in a workspace) and a small
+    reduce that sums the planes into the gradient (8-10 us each, ~36 per ZINC step, ~170 per TSP step).  Nothing reads
+    a weight gradient before the all-reduce / optimizer, so inside `with plan:` a weight gradient that ACCUMULATES into
+    its destination (`accumulate_into_grads`: the flat gradient bucket) only runs the first launch
+    (`hl_wgrad_deferred_tf32x3`) and leaves a descriptor here; `flush()` -- after `lanes.join()`, before the all-reduce --
+    sums all of them with `hl_wgrad_reduce_batch` (descriptors as kernel parameters: nothing to upload, capturable).
+    Two gradients for the same destination are not batched together: the second one is reduced on the spot."""
+
+    def __init__(self):
+        self.descs, self.keep, self.targets = [], [], set()
+
+    def __enter__(self):
+        global _RPLAN
+        assert _RPLAN is None, "WgradReducePlan scopes do not nest"
+        _RPLAN = self
+        return self
+
+    def __exit__(self, *a):
+        global _RPLAN
+        _RPLAN = None
+        if self.descs:
+            self.flush()
+
+    @staticmethod
+    def _extent(t):
+        rows, cols, ld = (1, t.shape[0], t.shape[0]) if t.dim() == 1 else (t.shape[0], t.shape[1], t.stride(0))
+        return t.data_ptr(), rows, cols, ld
+
+    @staticmethod
+    def _overlap(a, b):
+        if a[0] > b[0]:
+            a, b = b, a
+        (pa, ra, ca, la), (pb, rb, cb, lb) = a, b
+        if pa + ((ra - 1) * la + ca) * 4 <= pb:
+            return False                                          # disjoint address ranges
+        if la == lb and (pb - pa) % 4 == 0:                       # column blocks of one matrix (gw[:, :d] and gw[:, d:])
+            off = ((pb - pa) // 4) % la
+            if off >= ca and off + cb <= la:
+                return False
+        return True
+
+    def claim(self, *tensors):
+        """True when no destination overlaps one that is already pending in this batch (then they are registered)."""
+        ext = [self._extent(t) for t in tensors if t is not None]
+        if any(self._overlap(e, f) for e in ext for f in self.targets):
+            return False
+        self.targets.update(ext)
+        return True
+
+    def add(self, desc, *keep):
+        self.descs.append(desc)
+        self.keep.append(keep)                     # workspace (and operands) stay allocated until the reduce has run
+
+    def flush(self):
+        """Sum every pending weight gradient on the CURRENT stream (the caller has joined the streams the split-row
+        passes ran on)."""
+        if self.descs:
+            arr = (N.WgradReduceDesc * len(self.descs))(*self.descs)
+            N.check(N.lib().hl_wgrad_reduce_batch(arr, len(self.descs), N.stream_ptr()), "hl_wgrad_reduce_batch")
+            for keep in self.keep:                 # the allocator may hand the workspaces out again after this point
+                for t in keep:
+                    t.record_stream(torch.cuda.current_stream())
+        self.descs, self.keep, self.targets = [], [], set()
+
+
+_RPLAN = None
+_WGRAD_DEFER = _os.environ.get("HL_WGRAD_DEFER", "1") != "0"
+
+
+def _wgrad_deferred(g, ldg, x1, ldx1, x2, ldx2, out1, out2, bias_out, bias_accumulate):
+    """The split-row pass only, reduce left to the active WgradReducePlan.  Returns None when the gradient cannot be
+    deferred (no plan, shape outside the tensor-core path, destination already pending), else the rc of the launch
+    (0: all done later, 2: bias gradient not folded)."""
+    plan = _RPLAN
+    if plan is None or not _WGRAD_DEFER or not _GEMM_MODE["tensor"]:
+        return None
+    L = N.lib()
+    R, fo = g.shape
+    fi = x1.shape[1]
+    nb = L.hl_wgrad2_tf32x3_workspace(R, fo, fi) if x2 is not None else L.hl_wgrad_tf32x3_workspace(R, fo, fi)
+    if nb == 0:
+        return None
+    if not plan.claim(out1, out2, bias_out):
+        return None
+    ws = torch.empty(nb, dtype=torch.uint8, device=g.device)
+    desc = N.WgradReduceDesc()
+    rc = L.hl_wgrad_deferred_tf32x3(g.data_ptr(), ldg, x1.data_ptr(), ldx1, N.ptr(x2), ldx2, R, fo, fi, out1.data_ptr(), out1.stride(0),
+                                    N.ptr(out2), out2.stride(0) if out2 is not None else 0, 1, N.ptr(bias_out),
+                                    1 if bias_accumulate else 0, ws.data_ptr(), nb, C.byref(desc), N.stream_ptr())
+    if rc == 1:
+        return None
+    if rc not in (0, 2):
+        N.check(rc, "hl_wgrad_deferred_tf32x3")
+    plan.add(desc, ws)
+    return rc
+
+
 def wgrad(g, x, out=None, accumulate=False, bias_out=None, bias_accumulate=False):
     """dW[Fo,Fi] (=|+=) g[R,Fo]^T x[R,Fi] (deterministic split-row reduction); `out` may be a column slice.
     `bias_out` [Fo] (optional): also (=|+=) the column sums of g -- folded into the tensor-core launch when it can
@@ -386,6 +486,12 @@ def wgrad(g, x, out=None, accumulate=False, bias_out=None, bias_accumulate=False
         return out
     acc = 1 if accumulate else 0
     done = False
+    if accumulate and (bias_out is None or bias_accumulate):
+        rc = _wgrad_deferred(g, ldg, x, ldx, None, 0, out, None, bias_out, bias_accumulate)
+        if rc is not None:
+            if rc == 2 and bias_out is not None:
+                _colsum_into(g, ldg, bias_out, bias_accumulate)
+            return out
     if _GEMM_MODE["tensor"]:
         nb = L.hl_wgrad_tf32x3_workspace(R, fo, fi)
         ws = torch.empty(nb, dtype=torch.uint8, device=g.device)
@@ -418,6 +524,12 @@ def wgrad2(g, x1, x2, out1, out2, accumulate=False, bias_out=None, bias_accumula
         b, ldb = N.row_major(x2)
         R, fo = g2.shape
         fi = a.shape[1]
+        if accumulate and (bias_out is None or bias_accumulate):
+            rc = _wgrad_deferred(g2, ldg, a, lda, b, ldb, out1, out2, bias_out, bias_accumulate)
+            if rc is not None:
+                if rc == 2 and bias_out is not None:
+                    _colsum_into(g2, ldg, bias_out, bias_accumulate)
+                return out1, out2
         nb = L.hl_wgrad2_tf32x3_workspace(R, fo, fi)
         ws = torch.empty(nb, dtype=torch.uint8, device=g.device)
         acc = 1 if accumulate else 0

@@ -15,7 +15,7 @@ from types import SimpleNamespace
 import torch
 
 from . import lanes
-from .functional import accumulate_into_grads, WeightSplitPlan
+from .functional import accumulate_into_grads, WeightSplitPlan, WgradReducePlan
 from .simplex import clear_caches
 
 _PAD_KEYS = ("x_t", "x_s", "y", "edge_index", "edge_index_t", "edge_index_s", "edge_weight_t", "edge_weight_s",
@@ -178,6 +178,7 @@ class GraphedTrainStep:
         self.batch = StaticBatch(proto_batch, device)
         self.loss = torch.zeros((), device=device)
         self.split_plan = WeightSplitPlan() if warmup >= 2 else None     # recorded by the first warm-up step
+        self.reduce_plan = WgradReducePlan()
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
@@ -225,8 +226,9 @@ class GraphedTrainStep:
             g = self.batch.num_graphs
             pred = self.model(self.batch, device=self.device)
             loss = self.criterion(pred[:g], self.batch.y)
-        with accumulate_into_grads():              # weight gradients land in the flat bucket directly
-            loss.backward()
+        with self.reduce_plan:                     # ... their split reduces batched into one launch after the streams joined
+            with accumulate_into_grads():          # weight gradients land in the flat bucket directly
+                loss.backward()
         lanes.join(self.device)                     # edge-lane weight gradients land in the bucket before the all-reduce
         self.loss.copy_(loss.detach())
 

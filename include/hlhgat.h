@@ -398,6 +398,36 @@ int hl_wgrad2_bias_tf32x3(const float* g, int64_t ld_g, const float* x1, int64_t
                           int accumulate, float* dbias /* nullable */, int accumulate_bias, void* workspace,
                           size_t workspace_bytes, hl_stream_t stream);
 
+/* Deferred split reduce: hl_wgrad_deferred_tf32x3 launches only the tensor-core pass of a weight gradient (one activation:
+ * x2 = dw2 = NULL, or two that share g) and describes the pending reduce in *desc; `workspace` holds the partial planes and
+ * must live until hl_wgrad_reduce_batch has summed them.  A training step collects the descriptors of all its weight
+ * gradients (lib/Hodge_Cheb_Conv.py:487-510 and :277-288 backward, dozens per step) and reduces them in ONE launch before
+ * the all-reduce; two descriptors of one batch must not target the same elements.  `descs` is a host array. */
+typedef struct hl_wgrad_reduce_desc {
+  const float* partial;     /* [splits] planes of fo x fi, split_stride elements apart */
+  const float* cs_partial;  /* [2 splits][fo] column sums of g (bias gradient), used when dbias != NULL */
+  float* dw;                /* destination of columns [0, fi_first) (all columns when dw2 == NULL) */
+  float* dw2;               /* destination of columns [fi_first, fi), or NULL */
+  float* dbias;             /* or NULL */
+  int64_t split_stride;
+  int64_t ld_dw;
+  int64_t ld_dw2;
+  int32_t splits;
+  int32_t fo;
+  int32_t fi;               /* columns of a partial plane */
+  int32_t fi_first;
+  int32_t accumulate;
+  int32_t accumulate_bias;
+  int32_t block_start;      /* filled by hl_wgrad_reduce_batch */
+  int32_t reserved;
+} hl_wgrad_reduce_desc;
+int hl_wgrad_deferred_tf32x3(const float* g, int64_t ld_g, const float* x1, int64_t ld_x1, const float* x2 /* nullable */,
+                             int64_t ld_x2, int32_t nrows, int32_t fo, int32_t fi, float* dw1, int64_t ld_dw1,
+                             float* dw2 /* nullable */, int64_t ld_dw2, int accumulate, float* dbias /* nullable */,
+                             int accumulate_bias, void* workspace, size_t workspace_bytes, hl_wgrad_reduce_desc* desc,
+                             hl_stream_t stream);
+int hl_wgrad_reduce_batch(const hl_wgrad_reduce_desc* descs, int32_t n, hl_stream_t stream);
+
 /* --------------------------------------------------------------------------------------------
  * Weight and bias gradients of the dense layers as deterministic split-row reductions.
  *   hl_wgrad : dw[fo,fi] (=|+=) g[R,fo]^T x[R,fi]        hl_colsum : out[f] (=|+=) sum_r g[r,f]

@@ -119,3 +119,34 @@ def test_split_desc_layout_matches_header():
     body = re.search(r"typedef struct hl_split_desc \{(.*?)\} hl_split_desc;", header, re.S).group(1)
     names = re.findall(r"(\w+);", body)
     assert names == [f for f, _ in d._fields_]           # same members in the same order as the C declaration
+
+
+def test_wgrad_reduce_desc_layout_matches_header():
+    """hl_wgrad_reduce_desc as bound by ctypes: 5 pointers, 3 int64, 8 int32 = 96 bytes, same member order as the header
+    (functional.WgradReducePlan hands a host array of these to hl_wgrad_reduce_batch)."""
+    import ctypes as C
+    import re
+    from hlhgat_b200 import _native as N
+    d = N.WgradReduceDesc
+    assert C.sizeof(d) == 96
+    offs = [getattr(d, f).offset for f, _ in d._fields_]
+    assert offs == [0, 8, 16, 24, 32, 40, 48, 56, 64, 68, 72, 76, 80, 84, 88, 92]
+    header = open(os.path.join(ROOT, "include", "hlhgat.h")).read()
+    body = re.search(r"typedef struct hl_wgrad_reduce_desc \{(.*?)\} hl_wgrad_reduce_desc;", header, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"(\w+);", body)
+    assert names == [f for f, _ in d._fields_]
+
+
+def test_wgrad_reduce_plan_overlap_rule():
+    """Destinations of one batch: column blocks of one matrix do not conflict, the same view or a straddling one does."""
+    import torch
+    from hlhgat_b200.functional import WgradReducePlan
+    gw = torch.zeros(8, 12)
+    plan = WgradReducePlan()
+    assert plan.claim(gw[:, :4], gw[:, 4:8])
+    assert plan.claim(gw[:, 8:])
+    assert not plan.claim(gw[:, 2:6])
+    assert not plan.claim(gw)
+    assert not plan.claim(gw[:, :4])
+    assert plan.claim(torch.zeros(8), torch.zeros(3, 3))

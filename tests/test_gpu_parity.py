@@ -603,3 +603,53 @@ def test_training_step_with_and_without_epilogue_statistics(monkeypatch):
     # near-zero pre-activations); same bar as the fp32-vs-fp64 model tests, measured here at ~5e-4 relative
     for ga, gb in zip(out[0][1], out[1][1]):
         assert float((ga - gb).norm()) <= 5e-3 * float(gb.norm()) + 1e-7
+
+
+# ------------------------------------------------------------------------------------------
+# weight gradients with their split reduces batched into one launch (hl_wgrad_deferred_tf32x3 + hl_wgrad_reduce_batch)
+def test_deferred_weight_gradient_reduces_are_bit_identical():
+    g = torch.Generator().manual_seed(5)
+    shapes = [(24001, 64, 64), (5000, 128, 192), (3000, 256, 256), (24144, 256, 704), (700, 64, 96), (26232, 64, 32)]
+    shapes = shapes * 40                                                  # 240 descriptors: more than one parameter block
+    cases = []
+    for k, (R, fo, fi) in enumerate(shapes[:8]):
+        cases.append((torch.randn(R, fo, generator=g).to(DEV), torch.randn(R, fi, generator=g).to(DEV), torch.randn(R, fi, generator=g).to(DEV)))
+
+    def run(plan):
+        outs = []
+        ctx = plan if plan is not None else __import__("contextlib").nullcontext()
+        with ctx:
+            for k, (R, fo, fi) in enumerate(shapes):
+                gg, x1, x2 = cases[k % len(cases)]
+                if (gg.shape[0], gg.shape[1], x1.shape[1]) != (R, fo, fi):
+                    gg, x1, x2 = [c for c in cases if (c[0].shape[0], c[0].shape[1], c[1].shape[1]) == (R, fo, fi)][0]
+                w = torch.full((fo, 2 * fi), 0.5, device=DEV)
+                b = torch.full((fo,), -1.0, device=DEV)
+                if k % 3 == 0:
+                    F_hl.wgrad2(gg, x1, x2, w[:, :fi], w[:, fi:], accumulate=True, bias_out=b, bias_accumulate=True)
+                elif k % 3 == 1:
+                    F_hl.wgrad(gg, x1, w[:, :fi], accumulate=True, bias_out=b, bias_accumulate=True)
+                    F_hl.wgrad(gg, x2, w[:, fi:], accumulate=True)
+                else:
+                    F_hl.wgrad(gg, x1, w[:, :fi], accumulate=True)
+                    F_hl.wgrad(gg, x2, w[:, :fi], accumulate=True)        # same destination twice: the second is not deferred
+                outs.append((w, b))
+            if plan is not None:
+                assert len(plan.descs) > 192
+        torch.cuda.synchronize()
+        return outs
+
+    ref = run(None)
+    got = run(F_hl.WgradReducePlan())
+    for k, ((w0, b0), (w1, b1)) in enumerate(zip(ref, got)):
+        if k % 3 == 2:                          # (0.5 + a) + b against (0.5 + b) + a: the order of the two sums differs
+            close(w0, w1, rtol=1e-6, atol=1e-4)
+        else:
+            assert torch.equal(w0, w1) and torch.equal(b0, b1)
+    # and the values are right
+    gg, x1, x2 = cases[1]
+    k = 1
+    w, b = got[k]
+    fi = x1.shape[1]
+    close(w[:, :fi], 0.5 + (gg.double().t() @ x1.double()).float(), rtol=1e-5, atol=1e-3)
+    close(b, -1.0 + gg.double().sum(0).float(), rtol=1e-5, atol=1e-3)
