@@ -607,7 +607,8 @@ def test_training_step_with_and_without_epilogue_statistics(monkeypatch):
 
 # ------------------------------------------------------------------------------------------
 # weight gradients with their split reduces batched into one launch (hl_wgrad_deferred_tf32x3 + hl_wgrad_reduce_batch)
-def test_deferred_weight_gradient_reduces_are_bit_identical():
+def test_deferred_weight_gradient_reduces_are_bit_identical(monkeypatch):
+    monkeypatch.setattr(F_hl, "_WGRAD_DEFER", True)                       # opt-in path (HL_WGRAD_DEFER=1)
     g = torch.Generator().manual_seed(5)
     shapes = [(24001, 64, 64), (5000, 128, 192), (3000, 256, 256), (24144, 256, 704), (700, 64, 96), (26232, 64, 32)]
     shapes = shapes * 40                                                  # 240 descriptors: more than one parameter block
