@@ -34,6 +34,8 @@ template <int V>
 __global__ void __launch_bounds__(kBnThreads)
 bn_stats_partial_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows_cap, const int32_t* __restrict__ nvalid,
                         int32_t width, double* __restrict__ partial) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   const int32_t nrows = nvalid ? min(__ldg(nvalid), nrows_cap) : nrows_cap;
   __shared__ float sh[2][kBnWarps][32 * V];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -132,6 +134,8 @@ __global__ void bn_stats_final_kernel(const double* __restrict__ partial, int nb
                                       float* __restrict__ stats, float* __restrict__ running_mean,
                                       float* __restrict__ running_var, float momentum,
                                       long long* __restrict__ batches_tracked) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   if (batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *batches_tracked += 1;   // nn.BatchNorm1d.num_batches_tracked
   const int32_t nrows = nvalid ? min(__ldg(nvalid), nrows_cap) : nrows_cap;
   double a, b;
@@ -178,6 +182,8 @@ __global__ void __launch_bounds__(kBnTileCols* kBnTileSlices)
 bn_stats_final_tiles_kernel(const float* __restrict__ part, int32_t nrows_cap, const int32_t* __restrict__ nvalid,
                             int32_t width, float* __restrict__ stats, float* __restrict__ running_mean,
                             float* __restrict__ running_var, float momentum, long long* __restrict__ batches_tracked) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   if (batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *batches_tracked += 1;
   __shared__ double sh[kBnTileSlices / 8][kBnTileCols];
   // every load of the launch is issued up front (the row count and up to kBnTileHold (mean, M2) pairs per thread: enough
@@ -236,6 +242,8 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_apply_kernel(const float* __restrict__ x, int64_t ld_x, int32_t nrows, const int32_t* __restrict__ nvalid, int32_t width,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
                 float eps, float slope, float* __restrict__ y, int64_t ld_y) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   const int32_t nv = nvalid ? min(__ldg(nvalid), nrows) : nrows;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int chunks = (min(width - (int)blockIdx.y * (32 * V), 32 * V) + V - 1) / V;
@@ -281,6 +289,8 @@ bn_bwd_partial_kernel(const float* __restrict__ x, int64_t ld_x, const float* __
                       const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ dy2, int64_t ld_dy2,
                       int32_t nrows_cap, const int32_t* __restrict__ nvalid,
                       int32_t width, const float* __restrict__ stats, float eps, float slope, double* __restrict__ partial) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   __shared__ float sh[2][kBnWarps][32 * V];
   const int32_t nrows = nvalid ? min(__ldg(nvalid), nrows_cap) : nrows_cap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -361,6 +371,8 @@ bn_bwd_partial_kernel(const float* __restrict__ x, int64_t ld_x, const float* __
 __global__ void bn_bwd_final_kernel(const double* __restrict__ partial, int nblk, int32_t width,
                                     float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                     int accumulate) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   double a, b;
   int c;
   if (bn_column_sums(partial, nblk, width, a, b, c)) {
@@ -378,6 +390,8 @@ bn_bwd_apply_kernel(const float* __restrict__ x, int64_t ld_x, const float* __re
                     int32_t nrows, const int32_t* __restrict__ nvalid, int32_t width,
                     const float* __restrict__ gamma, const float* __restrict__ stats, const float* __restrict__ sums,
                     float eps, float slope, float* __restrict__ dx, int64_t ld_dx, const float* __restrict__ inv_count) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   const int32_t nv = nvalid ? min(__ldg(nvalid), nrows) : nrows;
   const float inv_n = inv_count ? __ldg(inv_count) : 1.f / (float)max(nv, 1);   // inv_count: 1 / rows over ALL ranks (SyncBN)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -455,17 +469,17 @@ extern "C" int hl_bn_act_fwd(const float* x, int64_t ld_x, int32_t nrows, int32_
   V = min(V, vec_for(y, ld_y, width, V));
   const int nblk = bn_row_blocks(nrows);
   dim3 grid(nblk, (width + 32 * V - 1) / (32 * V));
-  if (V == 4) bn_stats_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
-  else if (V == 2) bn_stats_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
-  else bn_stats_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
+  if (V == 4) hl::launch_pdl(bn_stats_partial_kernel<4>, grid, kBnThreads, 0, st, x, ld_x, nrows, nvalid, width, partial);
+  else if (V == 2) hl::launch_pdl(bn_stats_partial_kernel<2>, grid, kBnThreads, 0, st, x, ld_x, nrows, nvalid, width, partial);
+  else hl::launch_pdl(bn_stats_partial_kernel<1>, grid, kBnThreads, 0, st, x, ld_x, nrows, nvalid, width, partial);
   HL_LAUNCH_CHECK("bn_stats_partial_kernel");
-  bn_stats_final_kernel<<<(width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st>>>(partial, nblk, x, nrows, nvalid, width, stats,
+  hl::launch_pdl(bn_stats_final_kernel, (width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st, partial, nblk, x, nrows, nvalid, width, stats,
                                                                     running_mean, running_mean ? running_var : nullptr, momentum,
                                                                     reinterpret_cast<long long*>(num_batches_tracked));
   HL_LAUNCH_CHECK("bn_stats_final_kernel");
-  if (V == 4) bn_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
-  else if (V == 2) bn_apply_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
-  else bn_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  if (V == 4) hl::launch_pdl(bn_apply_kernel<4>, grid, kBnThreads, 0, st, x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else if (V == 2) hl::launch_pdl(bn_apply_kernel<2>, grid, kBnThreads, 0, st, x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else hl::launch_pdl(bn_apply_kernel<1>, grid, kBnThreads, 0, st, x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
   HL_LAUNCH_CHECK("bn_apply_kernel");
   return HL_OK;
 }
@@ -480,16 +494,15 @@ extern "C" int hl_bn_act_fwd_tiles(const float* x, int64_t ld_x, int32_t nrows, 
   using namespace hl;
   if (nrows < 1 || width < 1 || !x || !y || !stats || !bn_part) return HL_ERR_INVALID;
   cudaStream_t st = as_stream(stream);
-  bn_stats_final_tiles_kernel<<<(width + kBnTileCols - 1) / kBnTileCols, kBnTileCols * kBnTileSlices, 0, st>>>(
-      bn_part, nrows, nvalid, width, stats, running_mean, running_mean ? running_var : nullptr, momentum,
+  hl::launch_pdl(bn_stats_final_tiles_kernel, (width + kBnTileCols - 1) / kBnTileCols, kBnTileCols * kBnTileSlices, 0, st, bn_part, nrows, nvalid, width, stats, running_mean, running_mean ? running_var : nullptr, momentum,
       reinterpret_cast<long long*>(num_batches_tracked));
   HL_LAUNCH_CHECK("bn_stats_final_tiles_kernel");
   int V = vec_for(x, ld_x, width, 4);
   V = min(V, vec_for(y, ld_y, width, V));
   dim3 grid(bn_row_blocks(nrows), (width + 32 * V - 1) / (32 * V));
-  if (V == 4) bn_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
-  else if (V == 2) bn_apply_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
-  else bn_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  if (V == 4) hl::launch_pdl(bn_apply_kernel<4>, grid, kBnThreads, 0, st, x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else if (V == 2) hl::launch_pdl(bn_apply_kernel<2>, grid, kBnThreads, 0, st, x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else hl::launch_pdl(bn_apply_kernel<1>, grid, kBnThreads, 0, st, x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
   HL_LAUNCH_CHECK("bn_apply_kernel");
   return HL_OK;
 }
@@ -513,15 +526,15 @@ extern "C" int hl_bn_act_bwd(const float* x, int64_t ld_x, const float* y, int64
   V = min(V, vec_for(dy2, ld_dy2, width, V));
   V = min(V, vec_for(dx, ld_dx, width, V));
   dim3 grid(nblk, (width + 32 * V - 1) / (32 * V));
-  if (V == 4) bn_bwd_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
-  else if (V == 2) bn_bwd_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
-  else bn_bwd_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
+  if (V == 4) hl::launch_pdl(bn_bwd_partial_kernel<4>, grid, kBnThreads, 0, st, x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
+  else if (V == 2) hl::launch_pdl(bn_bwd_partial_kernel<2>, grid, kBnThreads, 0, st, x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
+  else hl::launch_pdl(bn_bwd_partial_kernel<1>, grid, kBnThreads, 0, st, x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
   HL_LAUNCH_CHECK("bn_bwd_partial_kernel");
-  bn_bwd_final_kernel<<<(width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st>>>(partial, nblk, width, sums, dgamma, dbeta, accumulate_param_grads);
+  hl::launch_pdl(bn_bwd_final_kernel, (width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st, partial, nblk, width, sums, dgamma, dbeta, accumulate_param_grads);
   HL_LAUNCH_CHECK("bn_bwd_final_kernel");
-  if (V == 4) bn_bwd_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
-  else if (V == 2) bn_bwd_apply_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
-  else bn_bwd_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
+  if (V == 4) hl::launch_pdl(bn_bwd_apply_kernel<4>, grid, kBnThreads, 0, st, x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
+  else if (V == 2) hl::launch_pdl(bn_bwd_apply_kernel<2>, grid, kBnThreads, 0, st, x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
+  else hl::launch_pdl(bn_bwd_apply_kernel<1>, grid, kBnThreads, 0, st, x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, nullptr);
   HL_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return HL_OK;
 }
@@ -540,11 +553,11 @@ extern "C" int hl_bn_stats(const float* x, int64_t ld_x, int32_t nrows, int32_t 
   const int V = vec_for(x, ld_x, width, 4);
   const int nblk = bn_row_blocks(nrows);
   dim3 grid(nblk, (width + 32 * V - 1) / (32 * V));
-  if (V == 4) bn_stats_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
-  else if (V == 2) bn_stats_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
-  else bn_stats_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, partial);
+  if (V == 4) hl::launch_pdl(bn_stats_partial_kernel<4>, grid, kBnThreads, 0, st, x, ld_x, nrows, nvalid, width, partial);
+  else if (V == 2) hl::launch_pdl(bn_stats_partial_kernel<2>, grid, kBnThreads, 0, st, x, ld_x, nrows, nvalid, width, partial);
+  else hl::launch_pdl(bn_stats_partial_kernel<1>, grid, kBnThreads, 0, st, x, ld_x, nrows, nvalid, width, partial);
   HL_LAUNCH_CHECK("bn_stats_partial_kernel");
-  bn_stats_final_kernel<<<(width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st>>>(partial, nblk, x, nrows, nvalid, width, stats,
+  hl::launch_pdl(bn_stats_final_kernel, (width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st, partial, nblk, x, nrows, nvalid, width, stats,
                                                                     nullptr, nullptr, 0.f, nullptr);
   HL_LAUNCH_CHECK("bn_stats_final_kernel");
   return HL_OK;
@@ -559,9 +572,9 @@ extern "C" int hl_bn_apply(const float* x, int64_t ld_x, int32_t nrows, int32_t 
   int V = vec_for(x, ld_x, width, 4);
   V = min(V, vec_for(y, ld_y, width, V));
   dim3 grid(bn_row_blocks(nrows), (width + 32 * V - 1) / (32 * V));
-  if (V == 4) bn_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
-  else if (V == 2) bn_apply_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
-  else bn_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  if (V == 4) hl::launch_pdl(bn_apply_kernel<4>, grid, kBnThreads, 0, st, x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else if (V == 2) hl::launch_pdl(bn_apply_kernel<2>, grid, kBnThreads, 0, st, x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
+  else hl::launch_pdl(bn_apply_kernel<1>, grid, kBnThreads, 0, st, x, ld_x, nrows, nvalid, width, gamma, beta, stats, eps, slope, y, ld_y);
   HL_LAUNCH_CHECK("bn_apply_kernel");
   return HL_OK;
 }
@@ -581,11 +594,11 @@ extern "C" int hl_bn_bwd_sums(const float* x, int64_t ld_x, const float* y, int6
   V = min(V, vec_for(y, ld_y, width, V));
   V = min(V, vec_for(dy, ld_dy, width, V));
   dim3 grid(nblk, (width + 32 * V - 1) / (32 * V));
-  if (V == 4) bn_bwd_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
-  else if (V == 2) bn_bwd_partial_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
-  else bn_bwd_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
+  if (V == 4) hl::launch_pdl(bn_bwd_partial_kernel<4>, grid, kBnThreads, 0, st, x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
+  else if (V == 2) hl::launch_pdl(bn_bwd_partial_kernel<2>, grid, kBnThreads, 0, st, x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
+  else hl::launch_pdl(bn_bwd_partial_kernel<1>, grid, kBnThreads, 0, st, x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, stats, eps, slope, partial);
   HL_LAUNCH_CHECK("bn_bwd_partial_kernel");
-  bn_bwd_final_kernel<<<(width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st>>>(partial, nblk, width, sums, nullptr, nullptr, 0);
+  hl::launch_pdl(bn_bwd_final_kernel, (width + kBnFinalCols - 1) / kBnFinalCols, 256, 0, st, partial, nblk, width, sums, nullptr, nullptr, 0);
   HL_LAUNCH_CHECK("bn_bwd_final_kernel");
   return HL_OK;
 }
@@ -604,9 +617,9 @@ extern "C" int hl_bn_bwd_apply(const float* x, int64_t ld_x, const float* y, int
   V = min(V, vec_for(dy, ld_dy, width, V));
   V = min(V, vec_for(dx, ld_dx, width, V));
   dim3 grid(bn_row_blocks(nrows), (width + 32 * V - 1) / (32 * V));
-  if (V == 4) bn_bwd_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
-  else if (V == 2) bn_bwd_apply_kernel<2><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
-  else bn_bwd_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
+  if (V == 4) hl::launch_pdl(bn_bwd_apply_kernel<4>, grid, kBnThreads, 0, st, x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
+  else if (V == 2) hl::launch_pdl(bn_bwd_apply_kernel<2>, grid, kBnThreads, 0, st, x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
+  else hl::launch_pdl(bn_bwd_apply_kernel<1>, grid, kBnThreads, 0, st, x, ld_x, y, ld_y, dy, ld_dy, dy2, ld_dy2, nrows, nvalid, width, gamma, stats, sums, eps, slope, dx, ld_dx, inv_count);
   HL_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return HL_OK;
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "hlhgat.h"
 
 namespace hl {
@@ -22,6 +23,47 @@ void count_launch();   // bumps the library-wide kernel launch counter (hl_launc
     cudaError_t _e = cudaGetLastError();                           \
     if (_e != cudaSuccess) return hl::record_cuda_error(_e, name); \
   } while (0)
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the attribute may start while its stream predecessor is
+// still running -- as soon as every CTA of the predecessor has executed pdl_trigger() or exited -- and must execute
+// pdl_wait() before it touches anything the predecessor wrote (the wait returns once the predecessor has completed and its
+// writes are visible; without the attribute both instructions are no-ops).  What overlaps is the launch latency and the
+// dependent's prologue (barrier init, TMEM allocation) with the predecessor's tail; stream capture records the edge as a
+// programmatic one.  HL_PDL=0 launches everything without the attribute.
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HL_PDL"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+template <typename... Exp, typename... Act>
+inline cudaError_t launch_pdl(void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Act&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Exp>(args)...);
+}
+#ifndef HL_PDL_EARLY_TRIGGER
+#define HL_PDL_EARLY_TRIGGER 0
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+#if HL_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+// for the kernels with a long tail after their last dependent-visible decision (GEMM: the epilogue): dependents may be
+// scheduled from here (HL_PDL_LATE_TRIGGER=0 at compile time: only when the grid has exited)
+#ifndef HL_PDL_LATE_TRIGGER
+#define HL_PDL_LATE_TRIGGER 1
+#endif
+__device__ __forceinline__ void pdl_trigger_late() {
+#if HL_PDL_LATE_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // One-time PER-DEVICE configuration (cudaFuncSetAttribute and the SM count belong to a device, not to the process):
 // `need()` is true the first time it is called with a given device current.

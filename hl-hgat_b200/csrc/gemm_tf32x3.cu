@@ -203,6 +203,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                    const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_a2,
                    const GemmParams P) {
   extern __shared__ __align__(1024) unsigned char gm_smem[];
+  hl::pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bn = P.bn, stages = P.stages;
   const uint32_t a_bytes = kGmBM * kGmBK * 4, b_bytes = (uint32_t)bn * kGmBK * 4;
@@ -245,6 +246,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  hl::pdl_wait();                                                    // everything above overlapped the predecessor's tail (common.cuh)
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
@@ -321,6 +323,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         gm_commit(&empty_bar[s]);                                   // frees the stage when these MMAs retire
       }
       gm_commit(acc_bar);
+      hl::pdl_trigger_late();                                        // all MMAs issued: only the epilogue is left
     }
   } else {
     // ------------------------------------ converters, then epilogue ------------------------------------
@@ -553,6 +556,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
                               const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_a2,
                               const __grid_constant__ CUtensorMap map_c, const GemmParams P) {
   extern __shared__ __align__(1024) unsigned char gm_smem[];
+  hl::pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bn = P.bn, stages = P.stages;
   const uint32_t a_bytes = kGmBM * kGmBK * 4, b_bytes = (uint32_t)bn * kGmBK * 4;
@@ -591,6 +595,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  hl::pdl_wait();                                                    // everything above overlapped the predecessor's tail (common.cuh)
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
@@ -640,6 +645,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
         }
         gm_commit(&acc_full[b]);
       }
+      hl::pdl_trigger_late();                                        // this CTA's last tile is issued: only its epilogue is left
     }
   } else if (warp < 6) {
     // ------------------------------------ A converters ------------------------------------
@@ -802,6 +808,8 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
 // x -> hi (low 13 mantissa bits cleared) and lo = x - hi; optional transpose: out[c, r] = split(src[r, c])
 __global__ void tf32_split_kernel(const float* __restrict__ src, int64_t ld_src, int32_t rows, int32_t cols, int transpose,
                                   float* __restrict__ hi, float* __restrict__ lo, int64_t ld_out) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   const int64_t n = (int64_t)rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
@@ -816,6 +824,8 @@ __global__ void tf32_split_kernel(const float* __restrict__ src, int64_t ld_src,
 // the same split for a whole table of weight views in one launch: blockIdx.y = table entry
 __global__ void __launch_bounds__(256)
 tf32_split_batch_kernel(const hl_split_desc* __restrict__ table) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   const hl_split_desc D = table[blockIdx.y];
   const int64_t n = (int64_t)D.rows * D.cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -868,7 +878,7 @@ extern "C" int hl_tf32_split(const float* src, int64_t ld_src, int32_t rows, int
   const int64_t n = (int64_t)rows * cols;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  tf32_split_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(src, ld_src, rows, cols, transpose, hi, lo, ld_out);
+  hl::launch_pdl(tf32_split_kernel, (int)blocks, 256, 0, as_stream(stream), src, ld_src, rows, cols, transpose, hi, lo, ld_out);
   HL_LAUNCH_CHECK("tf32_split_kernel");
   return HL_OK;
 }
@@ -880,7 +890,7 @@ extern "C" int hl_tf32_split_batch(const hl_split_desc* table, int32_t n_entries
   if (!table || n_entries > 65535) return HL_ERR_INVALID;
   int64_t bx = (max_elements + 255) / 256;
   if (bx > 32) bx = 32;
-  tf32_split_batch_kernel<<<dim3((unsigned)bx, (unsigned)n_entries), 256, 0, as_stream(stream)>>>(table);
+  hl::launch_pdl(tf32_split_batch_kernel, dim3((unsigned)bx, (unsigned)n_entries), 256, 0, as_stream(stream), table);
   HL_LAUNCH_CHECK("tf32_split_batch_kernel");
   return HL_OK;
 }
@@ -1018,7 +1028,7 @@ extern "C" int hl_gemm2_bn_tf32x3(const float* A, int64_t lda, int32_t K, const 
       const int sms = device_sm_count();
       const int grid_ps = Q.num_tiles < sms ? Q.num_tiles : sms;
       if (!c_map) pc = pa;
-      gemm_tf32x3_persistent_kernel<<<grid_ps, kPsThreads, smem_ps, as_stream(stream)>>>(pa, pbh, pbl, pa2, pc, Q);
+      hl::launch_pdl(gemm_tf32x3_persistent_kernel, grid_ps, kPsThreads, smem_ps, as_stream(stream), pa, pbh, pbl, pa2, pc, Q);
       HL_LAUNCH_CHECK("gemm_tf32x3_persistent_kernel");
       return HL_OK;
     }
@@ -1030,8 +1040,8 @@ extern "C" int hl_gemm2_bn_tf32x3(const float* A, int64_t lda, int32_t K, const 
   P.tmem_a_col = tmem_a_col; P.colsum_ws = nullptr; P.conv_groups = 1;
   P.kb_first = K2 > 0 ? kb_first : 0x7fffffff;
   dim3 grid((M + kGmBM - 1) / kGmBM, ntiles);
-  if (use_ts) gemm_tf32x3_kernel<0, 1><<<grid, 64 + kGmConvThreads, smem, as_stream(stream)>>>(ma, mbh, mbl, ma2, P);
-  else gemm_tf32x3_kernel<0, 0><<<grid, 64 + kGmConvThreads, smem, as_stream(stream)>>>(ma, mbh, mbl, ma2, P);
+  if (use_ts) hl::launch_pdl(gemm_tf32x3_kernel<0, 1>, grid, 64 + kGmConvThreads, smem, as_stream(stream), ma, mbh, mbl, ma2, P);
+  else hl::launch_pdl(gemm_tf32x3_kernel<0, 0>, grid, 64 + kGmConvThreads, smem, as_stream(stream), ma, mbh, mbl, ma2, P);
   HL_LAUNCH_CHECK("gemm_tf32x3_kernel");
   return HL_OK;
 }
@@ -1107,6 +1117,8 @@ gm_split_reduce_kernel(const float* __restrict__ partial, int32_t splits, int64_
                        int32_t fi, float* __restrict__ dw, int64_t ld_dw, int accumulate,
                        const float* __restrict__ cs_partial, float* __restrict__ dbias, int accumulate_bias,
                        float* __restrict__ dw2, int64_t ld_dw2, int32_t fi_first) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   const int64_t groups = gm_split_reduce_groups(fo, fi, dbias != nullptr);
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < groups; i += ((int64_t)gridDim.x * blockDim.x) >> 3)
     gm_split_reduce_group(partial, splits, split_stride, fo, fi, dw, ld_dw, accumulate, cs_partial, dbias, accumulate_bias, dw2,
@@ -1122,6 +1134,8 @@ struct ReduceBatch {
   hl_wgrad_reduce_desc d[kReduceBatchMax];
 };
 __global__ void __launch_bounds__(256) gm_split_reduce_batch_kernel(const __grid_constant__ ReduceBatch B) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   for (int blk = blockIdx.x; blk < B.total_blocks; blk += gridDim.x) {
     int lo = 0, hi = B.n - 1;
     while (lo < hi) {                                                // last descriptor whose first unit is <= blk
@@ -1266,8 +1280,8 @@ static int wgrad_launch(const float* g, int64_t ld_g, const float* x, int64_t ld
   P.colsum_ws = fold_bias ? cs_ws : nullptr; P.conv_groups = (use_ts && max_groups == 2 && stages % 2 == 0) ? 2 : 1;
   dim3 grid(mtiles, ntiles * nx, splits);
   P.kb_first = 0;
-  if (use_ts) gemm_tf32x3_kernel<1, 1><<<grid, 64 + P.conv_groups * kGmConvThreads, smem, as_stream(stream)>>>(mg, mx, mx2, mx, P);
-  else gemm_tf32x3_kernel<1, 0><<<grid, 64 + kGmConvThreads, smem, as_stream(stream)>>>(mg, mx, mx, mx, P);
+  if (use_ts) hl::launch_pdl(gemm_tf32x3_kernel<1, 1>, grid, 64 + P.conv_groups * kGmConvThreads, smem, as_stream(stream), mg, mx, mx2, mx, P);
+  else hl::launch_pdl(gemm_tf32x3_kernel<1, 0>, grid, 64 + kGmConvThreads, smem, as_stream(stream), mg, mx, mx, mx, P);
   HL_LAUNCH_CHECK("gemm_tf32x3_kernel<wgrad>");
   const int64_t n = (int64_t)fo * fi_tot;
   if (defer) {                                                       // the caller sums the splits later (hl_wgrad_reduce_batch)
@@ -1277,8 +1291,7 @@ static int wgrad_launch(const float* g, int64_t ld_g, const float* x, int64_t ld
     defer->accumulate = accumulate; defer->accumulate_bias = accumulate_bias; defer->block_start = 0; defer->reserved = 0;
     return (dbias && !fold_bias) ? 2 : HL_OK;
   }
-  gm_split_reduce_kernel<<<(int)(((n + (fold_bias ? fo : 0)) * 2 + 255) / 256), 256, 0, as_stream(stream)>>>(
-      P.C, splits, P.split_stride, fo, (int32_t)fi_tot, dw, ld_dw, accumulate, cs_ws, fold_bias ? dbias : nullptr, accumulate_bias,
+  hl::launch_pdl(gm_split_reduce_kernel, (int)(((n + (fold_bias ? fo : 0)) * 2 + 255) / 256), 256, 0, as_stream(stream), P.C, splits, P.split_stride, fo, (int32_t)fi_tot, dw, ld_dw, accumulate, cs_ws, fold_bias ? dbias : nullptr, accumulate_bias,
       dw2, ld_dw2, fi);
   HL_LAUNCH_CHECK("gm_split_reduce_kernel");
   return (dbias && !fold_bias) ? 2 : HL_OK;
@@ -1342,7 +1355,7 @@ extern "C" int hl_wgrad_reduce_batch(const hl_wgrad_reduce_desc* descs, int32_t 
     B.total_blocks = (int32_t)blocks;
     if (blocks == 0) continue;
     const int64_t max_grid = (int64_t)device_sm_count() * 8;
-    gm_split_reduce_batch_kernel<<<(int)(blocks < max_grid ? blocks : max_grid), 256, 0, as_stream(stream)>>>(B);
+    hl::launch_pdl(gm_split_reduce_batch_kernel, (int)(blocks < max_grid ? blocks : max_grid), 256, 0, as_stream(stream), B);
     HL_LAUNCH_CHECK("gm_split_reduce_batch_kernel");
   }
   return HL_OK;

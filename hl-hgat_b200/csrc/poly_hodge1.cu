@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(256)
 hodge1_node_kernel(const int32_t* __restrict__ inc_rowptr, const int32_t* __restrict__ inc_edge,
                    const int32_t* __restrict__ tail, const int32_t* __restrict__ head, int32_t n_nodes,
                    const float* __restrict__ x, int64_t ld_x, float* __restrict__ y, int32_t width, int32_t G) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   const int rows_per_block = 256 / G;
   const int gl = threadIdx.x & (G - 1);
   const int n = blockIdx.x * rows_per_block + (int)(threadIdx.x / G);
@@ -62,6 +64,8 @@ __global__ void __launch_bounds__(256)
 hodge1_edge_kernel(const int32_t* __restrict__ tail, const int32_t* __restrict__ head, int32_t n_edges,
                    const float* __restrict__ scale, const float* __restrict__ y, int32_t width, int32_t chunks,
                    const Hodge1Epi E) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   const int64_t total = (int64_t)n_edges * chunks;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -115,8 +119,8 @@ static int hodge1_apply(const hl_hodge1_operator& op, const float* xg, int64_t l
   const int G = group_lanes(width, V);
   const int gridn = (op.n_nodes + 256 / G - 1) / (256 / G);
   if (op.n_nodes > 0) {
-    if (V == 4) hodge1_node_kernel<4><<<gridn, 256, 0, st>>>(op.inc_rowptr, op.inc_edge, op.tail, op.head, op.n_nodes, xg, ld_xg, node_tmp, width, G);
-    else hodge1_node_kernel<1><<<gridn, 256, 0, st>>>(op.inc_rowptr, op.inc_edge, op.tail, op.head, op.n_nodes, xg, ld_xg, node_tmp, width, G);
+    if (V == 4) hl::launch_pdl(hodge1_node_kernel<4>, gridn, 256, 0, st, op.inc_rowptr, op.inc_edge, op.tail, op.head, op.n_nodes, xg, ld_xg, node_tmp, width, G);
+    else hl::launch_pdl(hodge1_node_kernel<1>, gridn, 256, 0, st, op.inc_rowptr, op.inc_edge, op.tail, op.head, op.n_nodes, xg, ld_xg, node_tmp, width, G);
     HL_LAUNCH_CHECK("hodge1_node_kernel");
   }
   const int chunks = width / V;
@@ -124,8 +128,8 @@ static int hodge1_apply(const hl_hodge1_operator& op, const float* xg, int64_t l
   if (blocks > 148LL * 32) blocks = 148LL * 32;
 #define HL_H1_CASE(EP)                                                                                               \
   case EP:                                                                                                           \
-    if (V == 4) hodge1_edge_kernel<4, EP><<<(int)blocks, 256, 0, st>>>(op.tail, op.head, op.n_edges, op.edge_scale, node_tmp, width, chunks, E); \
-    else hodge1_edge_kernel<1, EP><<<(int)blocks, 256, 0, st>>>(op.tail, op.head, op.n_edges, op.edge_scale, node_tmp, width, chunks, E);        \
+    if (V == 4) hl::launch_pdl(hodge1_edge_kernel<4, EP>, (int)blocks, 256, 0, st, op.tail, op.head, op.n_edges, op.edge_scale, node_tmp, width, chunks, E); \
+    else hl::launch_pdl(hodge1_edge_kernel<1, EP>, (int)blocks, 256, 0, st, op.tail, op.head, op.n_edges, op.edge_scale, node_tmp, width, chunks, E);        \
     break;
   switch (epi) {
     HL_H1_CASE(HL_EPI_LAGUERRE_FIRST)

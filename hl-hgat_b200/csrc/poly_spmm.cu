@@ -31,6 +31,8 @@ template <int V, int CH, int U, int EPI>
 __global__ void __launch_bounds__(kThreads)
 poly_spmm_kernel(const SpmmBatch b, const int32_t width, const int32_t G,
                  const float c0, const float c1, const float c2, const float c3) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   int pb = 0;
   while (pb + 1 < b.n && (int32_t)blockIdx.x >= b.block_start[pb + 1]) ++pb;
   const hl_spmm_problem& P = b.p[pb];
@@ -138,12 +140,12 @@ static void launch_epi(dim3 grid, cudaStream_t stream, const SpmmBatch& b, int32
                        float c0, float c1, float c2, float c3) {
   switch (epi) {
 #define HL_EPI_CASE(E) \
-  case E: poly_spmm_kernel<V, CH, U, E><<<grid, kThreads, 0, stream>>>(b, width, G, c0, c1, c2, c3); break;
+  case E: hl::launch_pdl(poly_spmm_kernel<V, CH, U, E>, grid, kThreads, 0, stream, b, width, G, c0, c1, c2, c3); break;
     HL_EPI_CASE(HL_EPI_LAGUERRE_FIRST)
     HL_EPI_CASE(HL_EPI_LAGUERRE_STEP)
     HL_EPI_CASE(HL_EPI_CHEB_FIRST)
     HL_EPI_CASE(HL_EPI_CHEB_STEP)
-    default: poly_spmm_kernel<V, CH, U, HL_EPI_LINCOMB><<<grid, kThreads, 0, stream>>>(b, width, G, c0, c1, c2, c3);
+    default: hl::launch_pdl(poly_spmm_kernel<V, CH, U, HL_EPI_LINCOMB>, grid, kThreads, 0, stream, b, width, G, c0, c1, c2, c3);
 #undef HL_EPI_CASE
   }
 }

@@ -211,6 +211,8 @@ template <int EPI>
 __global__ void __launch_bounds__(kStThreads, 1)
 poly_spmm_staged_kernel(const StagedBatch b, const int32_t width, const int32_t tile_rows, const int32_t total_tiles,
                         const float c0, const float c1, const float c2, const float c3) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StagedSmem& S = *reinterpret_cast<StagedSmem*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -360,7 +362,7 @@ int launch_poly_spmm_staged(const hl_spmm_problem* probs, int n, int32_t width, 
     static DeviceOnce configured;                                                                             \
     if (configured.need())                                                                                    \
       cudaFuncSetAttribute(poly_spmm_staged_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    poly_spmm_staged_kernel<E><<<grid, kStThreads, smem, stream>>>(b, width, tile_rows, tiles, c0, c1, c2, c3); \
+    hl::launch_pdl(poly_spmm_staged_kernel<E>, grid, kStThreads, smem, stream, b, width, tile_rows, tiles, c0, c1, c2, c3); \
   } break;
   switch (epi) {
     HL_ST_CASE(HL_EPI_LAGUERRE_FIRST)

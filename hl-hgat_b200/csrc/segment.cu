@@ -19,6 +19,8 @@ segment_reduce_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restr
                       const float* __restrict__ src, int64_t ld_src, const float* __restrict__ src_scale,
                       float* __restrict__ dst, int64_t ld_dst, int32_t width, int32_t G, int post,
                       const float* __restrict__ row_scale, float cscale) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   const int rows_per_block = kSegThreads / G;
   const int gl = threadIdx.x & (G - 1);
   const int row = blockIdx.x * rows_per_block + (int)(threadIdx.x / G);
@@ -119,6 +121,8 @@ segment_reduce_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __
                            const float* __restrict__ src, int64_t ld_src, const float* __restrict__ src_scale,
                            float* __restrict__ dst, int64_t ld_dst, int32_t width, int32_t G, int post,
                            const float* __restrict__ row_scale, float cscale) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   const int groups_per_block = kSegThreads / G;
   const int gl = threadIdx.x & (G - 1);
   const int r0 = (blockIdx.x * groups_per_block + (int)(threadIdx.x / G)) * RB;
@@ -219,6 +223,8 @@ __global__ void __launch_bounds__(256)
 endpoint_gather_kernel(const int32_t* __restrict__ tail, const int32_t* __restrict__ head, int32_t nedges,
                        const float* __restrict__ src, int64_t ld_src, const float* __restrict__ node_rcp,
                        float* __restrict__ dst, int64_t ld_dst, int32_t chunks, float cscale) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   const int64_t total = (int64_t)nedges * chunks;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -248,6 +254,8 @@ __global__ void __launch_bounds__(256)
 boundary_absdiff_fwd_kernel(const int32_t* __restrict__ tail, const int32_t* __restrict__ head, int32_t nedges,
                             const float* __restrict__ src, int64_t ld_src, float* __restrict__ dst, int64_t ld_dst,
                             int32_t chunks, float cscale) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   const int64_t total = (int64_t)nedges * chunks;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -270,6 +278,8 @@ boundary_absdiff_bwd_kernel(const int32_t* __restrict__ inc_rowptr, const int32_
                             const int32_t* __restrict__ tail, const int32_t* __restrict__ head, int32_t nnodes,
                             const float* __restrict__ src, int64_t ld_src, const float* __restrict__ g, int64_t ld_g,
                             float* __restrict__ dsrc, int64_t ld_dsrc, int32_t width, int32_t G, float cscale) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   const int rows_per_block = 256 / G;
   const int gl = threadIdx.x & (G - 1);
   const int n = blockIdx.x * rows_per_block + (int)(threadIdx.x / G);
@@ -309,6 +319,8 @@ owner_gather_kernel(const int32_t* __restrict__ owner, int32_t nsrc, const float
                     const float* __restrict__ owner_scale, const float* __restrict__ src_scale,
                     const float* __restrict__ src, int64_t ld_src, float* __restrict__ dsrc, int64_t ld_dsrc,
                     float* __restrict__ dscale, int32_t width, int32_t G) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   const int rows_per_block = 256 / G;
   const int gl = threadIdx.x & (G - 1);
   const int m = blockIdx.x * rows_per_block + (int)(threadIdx.x / G);
@@ -354,6 +366,8 @@ __global__ void __launch_bounds__(256)
 att_gate_fwd_kernel(const float* __restrict__ qc, const float* __restrict__ qs, const float* __restrict__ k,
                     int32_t nrows, int32_t dk, int32_t G, float lambda, float inv_sqrt_dk, int sigma,
                     float* __restrict__ a) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   const int rows_per_block = 256 / G;
   const int gl = threadIdx.x & (G - 1);
   const int r = blockIdx.x * rows_per_block + (int)(threadIdx.x / G);
@@ -384,6 +398,8 @@ att_gate_bwd_kernel(const float* __restrict__ qc, const float* __restrict__ qs, 
                     const float* __restrict__ a, const float* __restrict__ da, int32_t nrows, int32_t dk,
                     float lambda, float inv_sqrt_dk, int sigma,
                     float* __restrict__ dqc, float* __restrict__ dqs, float* __restrict__ dkk) {
+  hl::pdl_trigger();
+  hl::pdl_wait();   // programmatic dependent launch: see common.cuh
   const int chunks = dk / V;
   const int64_t total = (int64_t)nrows * chunks;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -447,7 +463,7 @@ extern "C" int hl_segment_reduce(const int32_t* rowptr, const int32_t* colidx, i
     const int groups = (nrows + RB - 1) / RB;
     dim3 grid_rb((groups + kSegThreads / G - 1) / (kSegThreads / G), (width + tile_w - 1) / tile_w);
 #define HL_SEGR_CASE(CC, RR)                                                                                   \
-    segment_reduce_rows_kernel<4, CC, RR><<<grid_rb, kSegThreads, 0, as_stream(stream)>>>(                        \
+    hl::launch_pdl(segment_reduce_rows_kernel<4, CC, RR>, grid_rb, kSegThreads, 0, as_stream(stream), \
         rowptr, colidx, nrows, src, ld_src, src_scale, dst, ld_dst, width, G, post, row_scale, cscale)
     if (RB == 8) { if (CH == 3) HL_SEGR_CASE(3, 8); else if (CH == 2) HL_SEGR_CASE(2, 8); else HL_SEGR_CASE(1, 8); }
     else { if (CH == 2) HL_SEGR_CASE(2, 4); else HL_SEGR_CASE(1, 4); }
@@ -456,7 +472,7 @@ extern "C" int hl_segment_reduce(const int32_t* rowptr, const int32_t* colidx, i
     return HL_OK;
   }
 #define HL_SEG_CASE(VV, CC)                                                                               \
-  segment_reduce_kernel<VV, CC><<<grid, kSegThreads, 0, as_stream(stream)>>>(                              \
+  hl::launch_pdl(segment_reduce_kernel<VV, CC>, grid, kSegThreads, 0, as_stream(stream), \
       rowptr, colidx, nrows, src, ld_src, src_scale, dst, ld_dst, width, G, post, row_scale, cscale)
   if (V == 4) { if (CH == 2) HL_SEG_CASE(4, 2); else HL_SEG_CASE(4, 1); }
   else if (V == 2) { if (CH == 2) HL_SEG_CASE(2, 2); else HL_SEG_CASE(2, 1); }
@@ -477,9 +493,9 @@ extern "C" int hl_endpoint_gather(const int32_t* tail, const int32_t* head, int3
   V = min(V, vec_for(dst, ld_dst, width, V));
   const int chunks = width / V;
   const int grid = grid_for((int64_t)nedges * chunks, 256);
-  if (V == 4) endpoint_gather_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(tail, head, nedges, src, ld_src, node_rcp, dst, ld_dst, chunks, cscale);
-  else if (V == 2) endpoint_gather_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(tail, head, nedges, src, ld_src, node_rcp, dst, ld_dst, chunks, cscale);
-  else endpoint_gather_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(tail, head, nedges, src, ld_src, node_rcp, dst, ld_dst, chunks, cscale);
+  if (V == 4) hl::launch_pdl(endpoint_gather_kernel<4>, grid, 256, 0, as_stream(stream), tail, head, nedges, src, ld_src, node_rcp, dst, ld_dst, chunks, cscale);
+  else if (V == 2) hl::launch_pdl(endpoint_gather_kernel<2>, grid, 256, 0, as_stream(stream), tail, head, nedges, src, ld_src, node_rcp, dst, ld_dst, chunks, cscale);
+  else hl::launch_pdl(endpoint_gather_kernel<1>, grid, 256, 0, as_stream(stream), tail, head, nedges, src, ld_src, node_rcp, dst, ld_dst, chunks, cscale);
   HL_LAUNCH_CHECK("endpoint_gather_kernel");
   return HL_OK;
 }
@@ -495,9 +511,9 @@ extern "C" int hl_boundary_absdiff_fwd(const int32_t* tail, const int32_t* head,
   V = min(V, vec_for(dst, ld_dst, width, V));
   const int chunks = width / V;
   const int grid = grid_for((int64_t)nedges * chunks, 256);
-  if (V == 4) boundary_absdiff_fwd_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(tail, head, nedges, src, ld_src, dst, ld_dst, chunks, cscale);
-  else if (V == 2) boundary_absdiff_fwd_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(tail, head, nedges, src, ld_src, dst, ld_dst, chunks, cscale);
-  else boundary_absdiff_fwd_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(tail, head, nedges, src, ld_src, dst, ld_dst, chunks, cscale);
+  if (V == 4) hl::launch_pdl(boundary_absdiff_fwd_kernel<4>, grid, 256, 0, as_stream(stream), tail, head, nedges, src, ld_src, dst, ld_dst, chunks, cscale);
+  else if (V == 2) hl::launch_pdl(boundary_absdiff_fwd_kernel<2>, grid, 256, 0, as_stream(stream), tail, head, nedges, src, ld_src, dst, ld_dst, chunks, cscale);
+  else hl::launch_pdl(boundary_absdiff_fwd_kernel<1>, grid, 256, 0, as_stream(stream), tail, head, nedges, src, ld_src, dst, ld_dst, chunks, cscale);
   HL_LAUNCH_CHECK("boundary_absdiff_fwd_kernel");
   return HL_OK;
 }
@@ -515,9 +531,9 @@ extern "C" int hl_boundary_absdiff_bwd(const int32_t* inc_rowptr, const int32_t*
   V = min(V, vec_for(dsrc, ld_dsrc, width, V));
   const int G = group_lanes(width, V);
   const int grid = (nnodes + 256 / G - 1) / (256 / G);
-  if (V == 4) boundary_absdiff_bwd_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(inc_rowptr, inc_edge, tail, head, nnodes, src, ld_src, g, ld_g, dsrc, ld_dsrc, width, G, cscale);
-  else if (V == 2) boundary_absdiff_bwd_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(inc_rowptr, inc_edge, tail, head, nnodes, src, ld_src, g, ld_g, dsrc, ld_dsrc, width, G, cscale);
-  else boundary_absdiff_bwd_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(inc_rowptr, inc_edge, tail, head, nnodes, src, ld_src, g, ld_g, dsrc, ld_dsrc, width, G, cscale);
+  if (V == 4) hl::launch_pdl(boundary_absdiff_bwd_kernel<4>, grid, 256, 0, as_stream(stream), inc_rowptr, inc_edge, tail, head, nnodes, src, ld_src, g, ld_g, dsrc, ld_dsrc, width, G, cscale);
+  else if (V == 2) hl::launch_pdl(boundary_absdiff_bwd_kernel<2>, grid, 256, 0, as_stream(stream), inc_rowptr, inc_edge, tail, head, nnodes, src, ld_src, g, ld_g, dsrc, ld_dsrc, width, G, cscale);
+  else hl::launch_pdl(boundary_absdiff_bwd_kernel<1>, grid, 256, 0, as_stream(stream), inc_rowptr, inc_edge, tail, head, nnodes, src, ld_src, g, ld_g, dsrc, ld_dsrc, width, G, cscale);
   HL_LAUNCH_CHECK("boundary_absdiff_bwd_kernel");
   return HL_OK;
 }
@@ -535,9 +551,9 @@ extern "C" int hl_owner_gather(const int32_t* owner, int32_t nsrc, const float* 
   V = min(V, vec_for(dscale ? src : nullptr, ld_src, width, V));
   const int G = group_lanes(width, V);
   const int grid = (nsrc + 256 / G - 1) / (256 / G);
-  if (V == 4) owner_gather_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(owner, nsrc, g, ld_g, owner_scale, src_scale, src, ld_src, dsrc, ld_dsrc, dscale, width, G);
-  else if (V == 2) owner_gather_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(owner, nsrc, g, ld_g, owner_scale, src_scale, src, ld_src, dsrc, ld_dsrc, dscale, width, G);
-  else owner_gather_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(owner, nsrc, g, ld_g, owner_scale, src_scale, src, ld_src, dsrc, ld_dsrc, dscale, width, G);
+  if (V == 4) hl::launch_pdl(owner_gather_kernel<4>, grid, 256, 0, as_stream(stream), owner, nsrc, g, ld_g, owner_scale, src_scale, src, ld_src, dsrc, ld_dsrc, dscale, width, G);
+  else if (V == 2) hl::launch_pdl(owner_gather_kernel<2>, grid, 256, 0, as_stream(stream), owner, nsrc, g, ld_g, owner_scale, src_scale, src, ld_src, dsrc, ld_dsrc, dscale, width, G);
+  else hl::launch_pdl(owner_gather_kernel<1>, grid, 256, 0, as_stream(stream), owner, nsrc, g, ld_g, owner_scale, src_scale, src, ld_src, dsrc, ld_dsrc, dscale, width, G);
   HL_LAUNCH_CHECK("owner_gather_kernel");
   return HL_OK;
 }
@@ -554,9 +570,9 @@ extern "C" int hl_att_gate_fwd(const float* qc, const float* qs, const float* k,
   const int G = group_lanes(dk, V);
   const int grid = (nrows + 256 / G - 1) / (256 / G);
   const float isd = 1.f / sqrtf((float)dk);
-  if (V == 4) att_gate_fwd_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(qc, qs, k, nrows, dk, G, lambda, isd, sigma, a);
-  else if (V == 2) att_gate_fwd_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(qc, qs, k, nrows, dk, G, lambda, isd, sigma, a);
-  else att_gate_fwd_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(qc, qs, k, nrows, dk, G, lambda, isd, sigma, a);
+  if (V == 4) hl::launch_pdl(att_gate_fwd_kernel<4>, grid, 256, 0, as_stream(stream), qc, qs, k, nrows, dk, G, lambda, isd, sigma, a);
+  else if (V == 2) hl::launch_pdl(att_gate_fwd_kernel<2>, grid, 256, 0, as_stream(stream), qc, qs, k, nrows, dk, G, lambda, isd, sigma, a);
+  else hl::launch_pdl(att_gate_fwd_kernel<1>, grid, 256, 0, as_stream(stream), qc, qs, k, nrows, dk, G, lambda, isd, sigma, a);
   HL_LAUNCH_CHECK("att_gate_fwd_kernel");
   return HL_OK;
 }
@@ -573,9 +589,9 @@ extern "C" int hl_att_gate_bwd(const float* qc, const float* qs, const float* k,
   for (auto p : ps) V = min(V, vec_for(p, dk, dk, V));
   const int grid = grid_for((int64_t)nrows * (dk / V), 256);
   const float isd = 1.f / sqrtf((float)dk);
-  if (V == 4) att_gate_bwd_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(qc, qs, k, a, da, nrows, dk, lambda, isd, sigma, dqc, dqs, dkk);
-  else if (V == 2) att_gate_bwd_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(qc, qs, k, a, da, nrows, dk, lambda, isd, sigma, dqc, dqs, dkk);
-  else att_gate_bwd_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(qc, qs, k, a, da, nrows, dk, lambda, isd, sigma, dqc, dqs, dkk);
+  if (V == 4) hl::launch_pdl(att_gate_bwd_kernel<4>, grid, 256, 0, as_stream(stream), qc, qs, k, a, da, nrows, dk, lambda, isd, sigma, dqc, dqs, dkk);
+  else if (V == 2) hl::launch_pdl(att_gate_bwd_kernel<2>, grid, 256, 0, as_stream(stream), qc, qs, k, a, da, nrows, dk, lambda, isd, sigma, dqc, dqs, dkk);
+  else hl::launch_pdl(att_gate_bwd_kernel<1>, grid, 256, 0, as_stream(stream), qc, qs, k, a, da, nrows, dk, lambda, isd, sigma, dqc, dqs, dkk);
   HL_LAUNCH_CHECK("att_gate_bwd_kernel");
   return HL_OK;
 }
