@@ -654,3 +654,27 @@ def test_deferred_weight_gradient_reduces_are_bit_identical(monkeypatch):
     fi = x1.shape[1]
     close(w[:, :fi], 0.5 + (gg.double().t() @ x1.double()).float(), rtol=1e-5, atol=1e-3)
     close(b, -1.0 + gg.double().sum(0).float(), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("M,Nn,K", [(38001, 64, 64), (40033, 48, 96), (20001, 416, 128), (9000, 800, 64), (38017, 128, 32),
+                                    (12345, 672, 128), (300, 64, 64)])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_gemm_output_slice_is_written_exactly(M, Nn, K, accumulate):
+    """The persistent kernel's TMA-store / TMA-reduce epilogue (and the register epilogue of the one-tile kernel) write the
+    [M, N] slice of a wider, taller buffer and nothing around it: ragged row tiles, column tiles that are not multiples of
+    32 (N = 416 -> 112-column tiles), N = 48."""
+    g = torch.Generator().manual_seed(M + Nn)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(Nn, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(Nn, generator=g).to(DEV)
+    big = torch.full((M + 70, Nn + 64), 7.25, device=DEV)
+    out = big[3:3 + M, 32:32 + Nn]                              # 16-byte aligned start, row pitch N + 64
+    if accumulate:
+        out.copy_(torch.arange(M, device=DEV, dtype=torch.float32).remainder(5).unsqueeze(1).expand(M, Nn))
+    old = out.clone()
+    F_hl.dense(a, w, bias, out=out, accumulate=accumulate)
+    ref = (a.double() @ w.double().t() + bias.double()).float() + (old if accumulate else 0.0)
+    close(out, ref, rtol=1e-5, atol=2e-5)
+    guard = big.clone()
+    guard[3:3 + M, 32:32 + Nn] = 7.25
+    assert bool((guard == 7.25).all())                          # nothing outside the slice was touched
