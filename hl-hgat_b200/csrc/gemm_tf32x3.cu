@@ -993,10 +993,11 @@ extern "C" int hl_gemm2_bn_tf32x3(const float* A, int64_t lda, int32_t K, const 
   // memory and two accumulators + the A slots inside the 512 TMEM columns
   static int persistent = -1;
   if (persistent < 0) { const char* e = getenv("HL_GEMM_PERSISTENT"); persistent = e ? atoi(e) : 1; }
-  // ... and more tiles than the one-tile kernel keeps resident at once (2 CTAs per SM): below that every tile of the
-  // one-tile kernel starts immediately, while 148 persistent CTAs would walk ceil(tiles / 148) tiles one after another
-  // (measured: [24144,64] x [64,64] 5.6 vs 6.4 us, [24144,256] x [256,256] 25.2 vs 18.4 us)
-  if (persistent && use_ts && bn <= 128 && (persistent == 2 || ctas > 2 * 148)) {
+  // Every forward / data-gradient launch takes it.  Before the TMA-store epilogue the one-tile kernel was faster up to the
+  // 296 tiles it keeps resident at once ([24144,64] x [64,64]: 5.6 vs 6.4 us) and HL_GEMM_PERSISTENT=2 restores that rule;
+  // with eight epilogue warps and asynchronous stores the persistent kernel wins there too -- same-box A/B of the whole
+  // step, 4 alternating runs: ZINC 4.446 -> 4.382 ms, CIFAR 15.22 -> 15.04, zinc_default 10.90 -> 10.79, TSP unchanged.
+  if (persistent && use_ts && bn <= 128 && (persistent != 2 || ctas > 2 * 148)) {
     const int acc_stride = (bn + 31) / 32 * 32;
     int ps = (int)((227 * 1024 - 1024 - kPsEpiWarps * kPsStageFloats * 4 - 256) / stage_bytes);
     if (ps > 6) ps = 6;
