@@ -150,3 +150,20 @@ def test_wgrad_reduce_plan_overlap_rule():
     assert not plan.claim(gw)
     assert not plan.claim(gw[:, :4])
     assert plan.claim(torch.zeros(8), torch.zeros(3, 3))
+
+
+def test_bn_epilogue_request_is_served_once_and_scoped():
+    """functional.bn_stats_from_epilogue: the request is visible to the first taker inside the `with`, gone afterwards,
+    restored on exit, and absent when disabled; a BnTiles without statistics never matches."""
+    import torch
+    from hlhgat_b200 import functional as F
+    assert F._take_bn_request() is None
+    with F.bn_stats_from_epilogue(None) as req:
+        assert (req is not None) == F._BN_EPILOGUE
+        first = F._take_bn_request()
+        assert first is req and F._take_bn_request() is None
+        with F.bn_stats_from_epilogue(None, enabled=False) as inner:
+            assert inner is None and F._take_bn_request() is None
+    assert F._take_bn_request() is None
+    if req is not None:
+        assert not req.matches(torch.zeros(4, 4), None)
