@@ -2,6 +2,7 @@
 lib/Hodge_ST_Model.py so existing checkpoints load with strict=True.  Only the classes the
 BASELINE.json configs drive are mirrored here."""
 import contextlib
+import os
 
 import torch
 import torch.nn as nn
@@ -11,6 +12,9 @@ from .. import lanes as _lanes
 from ..dense_stack import new_stack
 from ..simplex import Hodge1Factor, incidence_for, operator_for
 from .Hodge_Cheb_Conv import NEConv, NodeEdgeInt, adj2par1, degree, _bn_relu, _epilogue_stats, node_edge_int_on_stack
+
+
+_PARALLEL_BUCKETING = os.environ.get("HL_PARALLEL_BUCKETING", "1") != "0"
 
 
 def _share_tables(ln, op_s, inc):
@@ -71,17 +75,24 @@ class HL_HGCNN_zinc_dense_int3_pyr(nn.Module):
         # fixed-capacity (CUDA-graph) batches carry device-side valid counts; rows beyond are padding
         nv = (getattr(data, "n_valid_nodes", None), getattr(data, "n_valid_edges", None))
         nv_g = getattr(data, "n_valid_graphs", None)
-        # operators are bucketed once per batch; every layer below reuses the CSR tables
-        op_t = operator_for(data.edge_index_t, data.edge_weight_t, n)
-        op_s = operator_for(data.edge_index_s, data.edge_weight_s, e)
-        seg_t = F_hl.Segments.from_counts(torch.as_tensor(data.num_node1, device=x_t.device), total=n, ghost_last=nv_g is not None)
-        seg_s = F_hl.Segments.from_counts(torch.as_tensor(data.num_edge1, device=x_t.device), total=e, ghost_last=nv_g is not None)
-        inc = incidence_for(data.edge_index, n)
-        D = getattr(data, "D", None)
-        if D is None:
-            D = inc.degree()                # = degree(edge_index.view(-1)) of :624 (no 1e-6 in this model)
         with _lanes.open_lanes(x_t.device) as ln:      # ln is None unless lanes.enable_lanes(): single stream
-            _share_tables(ln, op_s, inc)
+            # operators are bucketed once per batch; every layer below reuses the CSR tables.  With lanes the edge lane
+            # buckets its own operator (only it reads L1) while the node lane does L0, the incidence tables and the
+            # segments: the serial prefix of the step is the longer of the two, not their sum.  The edge lane first
+            # meets the incidence tables after the exchange of the first NodeEdgeInt, which orders it behind them.
+            with (ln.edge_ctx() if ln is not None and _PARALLEL_BUCKETING else contextlib.nullcontext()):
+                op_s = operator_for(data.edge_index_s, data.edge_weight_s, e)
+            op_t = operator_for(data.edge_index_t, data.edge_weight_t, n)
+            inc = incidence_for(data.edge_index, n)
+            D = getattr(data, "D", None)
+            if D is None:
+                D = inc.degree()            # = degree(edge_index.view(-1)) of :624 (no 1e-6 in this model)
+            seg_t = F_hl.Segments.from_counts(torch.as_tensor(data.num_node1, device=x_t.device), total=n, ghost_last=nv_g is not None)
+            seg_s = F_hl.Segments.from_counts(torch.as_tensor(data.num_edge1, device=x_t.device), total=e, ghost_last=nv_g is not None)
+            if ln is not None and _PARALLEL_BUCKETING:
+                ln._mark(ln.edge, [inc.tail, inc.head, inc.rowptr, inc.edge, D])     # read on the edge lane later (no wait here)
+            else:
+                _share_tables(ln, op_s, inc)
             last = (len(self.channels) - 1, self.channels[-1] - 1)
             # dense connections in preallocated buffers: no torch.cat, every block transferred once (dense_stack.py);
             # the block of the last layer is never read (:627-636) and stays out of the buffers
